@@ -1,0 +1,250 @@
+// K4: alpha compositing (raw2outputs, reference nerf/models/model_utils.py:33-100) and its
+// analytic backward.  One warp per ray; sample s of a ray lives in lane s%32, chunk s/32, so
+// every global access is a fully coalesced 128 B (z, weights) or 512 B (raw float4) warp
+// transaction.  The exclusive transmittance product is a warp scan per 32-sample chunk with a
+// running carry.  HBM-bound: 20 B read (+4 noise) and 4 B written per sample, 28 B per ray.
+//
+// Numerics follow torch-CPU op for op (no FMA contraction; expf/division correctly rounded
+// variants).  torch.cumprod accumulates fp32 input in DOUBLE and rounds every output
+// (ATen cpu_cum_base_kernel, acc_type<float,false>), so the scan runs in fp64 as well: the
+// transmittance then matches the reference bit for bit except where a 1e-16 relative
+// difference in the double product straddles an fp32 rounding boundary.
+#include "nwx_common.cuh"
+
+namespace nwx {
+
+constexpr int kCompWarps = 8;   // warps (= rays) per block
+
+__device__ __forceinline__ double warp_incl_prod(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v *= up;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_incl_sum(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v += up;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_rn(float x) {        // torch.sigmoid: 1/(1+exp(-x))
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+struct RaySample {
+  float c[3];     // sigmoid(raw rgb)
+  float alpha;    // 1 - exp(-relu(sigma+noise)*dist)
+  float e;        // exp(-relu(sigma+noise)*dist) = 1 - alpha before rounding of the subtraction
+  float t;        // 1 - alpha + 1e-10
+  float dist;
+  float z;
+  bool pos;       // sigma + noise > 0
+};
+
+// Loads chunk j of a ray and evaluates the per-sample terms of model_utils.py:49-71.
+template <int K>
+__device__ __forceinline__ void load_ray(const float* __restrict__ raw, const float* __restrict__ z,
+                                         const float* __restrict__ noise, int64_t ray, int S, int lane,
+                                         float dnorm, RaySample (&sm)[K]) {
+  float zr[K];
+  float4 rw[K];
+  float nz[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {                                 // issue every load before any math
+    const int s = j * 32 + lane;
+    const bool ok = s < S;
+    const int64_t idx = ray * S + (ok ? s : S - 1);
+    zr[j] = ldg_stream(z + idx);
+    rw[j] = ldg_stream4(reinterpret_cast<const float4*>(raw) + idx);
+    nz[j] = noise ? ldg_stream(noise + idx) : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int s = j * 32 + lane;
+    float znext = __shfl_down_sync(kFull, zr[j], 1);
+    const float zhead = __shfl_sync(kFull, zr[(j + 1 < K) ? j + 1 : j], 0);
+    if (lane == 31) znext = zhead;
+    float dist = (s >= S - 1) ? 1e10f : __fsub_rn(znext, zr[j]);          // :51,:56
+    dist = __fmul_rn(dist, dnorm);                                        // :60
+    const float sg = noise ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
+    const float r = fmaxf(sg, 0.0f);
+    const float e = expf(__fmul_rn(-r, dist));                            // :49
+    RaySample& o = sm[j];
+    o.pos = sg > 0.0f;
+    o.e = e;
+    o.alpha = __fsub_rn(1.0f, e);
+    o.t = __fadd_rn(__fsub_rn(1.0f, o.alpha), 1e-10f);                    // :75
+    o.c[0] = sigmoidf_rn(rw[j].x); o.c[1] = sigmoidf_rn(rw[j].y); o.c[2] = sigmoidf_rn(rw[j].z);  // :62
+    o.dist = dist;
+    o.z = zr[j];
+    if (s >= S) { o.alpha = 0.0f; o.t = 1.0f; o.e = 1.0f; o.pos = false; }   // padding lanes: neutral
+  }
+}
+
+__device__ __forceinline__ float ray_dnorm(const float* __restrict__ rays_d, int d_stride, int64_t ray) {
+  const float dx = __ldg(rays_d + ray * d_stride + 0), dy = __ldg(rays_d + ray * d_stride + 1),
+              dz = __ldg(rays_d + ray * d_stride + 2);
+  return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));   // torch.norm, :60
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                     const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
+                     int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
+                     float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
+                     int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  int bad = 0;
+  for (int64_t ray = warp0; ray < N; ray += nwarps) {
+    RaySample sm[K];
+    load_ray<K>(raw, z, noise, ray, S, lane, ray_dnorm(rays_d, d_stride, ray), sm);
+    double carry = 1.0;
+    float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const double incl = warp_incl_prod((double)sm[j].t, lane);
+      double excl = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) excl = 1.0;
+      const float T = (float)(carry * excl);                              // :75 (cumprod, exclusive)
+      carry *= __shfl_sync(kFull, incl, 31);
+      const float w = __fmul_rn(sm[j].alpha, T);
+      const int s = j * 32 + lane;
+      if (s < S) {
+        if (weights) weights[ray * S + s] = w;
+        a_r += __fmul_rn(w, sm[j].c[0]); a_g += __fmul_rn(w, sm[j].c[1]); a_b += __fmul_rn(w, sm[j].c[2]);
+        a_d += __fmul_rn(w, sm[j].z);
+        a_w += w;
+      }
+    }
+    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);        // :84
+    a_d = warp_sum(a_d); a_w = warp_sum(a_w);                             // :93,:95
+    if (lane == 0) {
+      const float q = __fdiv_rn(a_d, a_w);                               // :94; 0/0 = NaN on empty rays and
+      const float dspv = __fdiv_rn(1.0f, (q != q) ? q : fmaxf(1e-10f, q));   // torch.max propagates NaN
+      if (white_bkgd) {                                                   // :98
+        const float bg = __fsub_rn(1.0f, a_w);
+        a_r = __fadd_rn(a_r, bg); a_g = __fadd_rn(a_g, bg); a_b = __fadd_rn(a_b, bg);
+      }
+      rgb[ray * 3 + 0] = a_r; rgb[ray * 3 + 1] = a_g; rgb[ray * 3 + 2] = a_b;
+      if (disp) disp[ray] = dspv;
+      if (acc) acc[ray] = a_w;
+      if (depth) depth[ray] = a_d;
+      const float chk[6] = {a_r, a_g, a_b, dspv, a_w, a_d};
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        if (chk[q] != chk[q]) bad |= 1;
+        else if (fabsf(chk[q]) == INFINITY) bad |= 2;
+      }
+    }
+  }
+  if (flags && bad) atomicOr(flags, bad);
+}
+
+// Backward: d(loss)/d(raw) from d(loss)/d(rgb_map).  With w_i = alpha_i T_i, T_i = prod_{j<i} t_j,
+// t_j = 1 - alpha_j + 1e-10 and G_i = g . c_i (minus sum(g) under a white background):
+//   dL/dalpha_i = G_i T_i - (sum_{k>i} G_k w_k) / t_i
+//   dL/dsigma_i = dL/dalpha_i * dist_i * exp(-relu(sigma_i) dist_i) * [sigma_i > 0]
+//   dL/draw_c_i = w_i g_c * c_ic (1 - c_ic)
+template <int K>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                     const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
+                     const float* __restrict__ d_rgb, int64_t N, int S, int white_bkgd,
+                     float* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  for (int64_t ray = warp0; ray < N; ray += nwarps) {
+    RaySample sm[K];
+    load_ray<K>(raw, z, noise, ray, S, lane, ray_dnorm(rays_d, d_stride, ray), sm);
+    const float g0 = __ldg(d_rgb + ray * 3 + 0), g1 = __ldg(d_rgb + ray * 3 + 1), g2 = __ldg(d_rgb + ray * 3 + 2);
+    const float gbg = white_bkgd ? (g0 + g1 + g2) : 0.0f;
+    float T[K], w[K], G[K];
+    double pre[K];     // inclusive prefix of G_k w_k
+    double carry = 1.0, run = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const double incl = warp_incl_prod((double)sm[j].t, lane);
+      double excl = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) excl = 1.0;
+      T[j] = (float)(carry * excl);
+      carry *= __shfl_sync(kFull, incl, 31);
+      w[j] = sm[j].alpha * T[j];
+      G[j] = g0 * sm[j].c[0] + g1 * sm[j].c[1] + g2 * sm[j].c[2] - gbg;
+      const double gw = (j * 32 + lane < S) ? (double)G[j] * (double)w[j] : 0.0;
+      const double inc = warp_incl_sum(gw, lane);
+      pre[j] = run + inc;
+      run += __shfl_sync(kFull, inc, 31);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int s = j * 32 + lane;
+      if (s < S) {
+        const float suffix = (float)(run - pre[j]);
+        const float dalpha = G[j] * T[j] - suffix / sm[j].t;
+        const float dsig = sm[j].pos ? dalpha * sm[j].dist * sm[j].e : 0.0f;
+        float4 o;
+        o.x = w[j] * g0 * sm[j].c[0] * (1.0f - sm[j].c[0]);
+        o.y = w[j] * g1 * sm[j].c[1] * (1.0f - sm[j].c[1]);
+        o.z = w[j] * g2 * sm[j].c[2] * (1.0f - sm[j].c[2]);
+        o.w = dsig;
+        reinterpret_cast<float4*>(d_raw)[ray * S + s] = o;
+      }
+    }
+  }
+}
+
+static inline unsigned comp_grid(int64_t N) {
+  int64_t blocks = (N + kCompWarps - 1) / kCompWarps;
+  const int64_t cap = (int64_t)num_sms() * 8;     // 8 blocks x 8 warps = 64 resident warps per SM
+  return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace nwx
+
+#define NWX_DISPATCH_K(S, CALL)                       \
+  switch (((S) + 31) / 32) {                          \
+    case 1: { constexpr int K = 1; CALL; } break;     \
+    case 2: { constexpr int K = 2; CALL; } break;     \
+    case 3: { constexpr int K = 3; CALL; } break;     \
+    case 4: { constexpr int K = 4; CALL; } break;     \
+    case 5: { constexpr int K = 5; CALL; } break;     \
+    case 6: { constexpr int K = 6; CALL; } break;     \
+    case 7: { constexpr int K = 7; CALL; } break;     \
+    case 8: { constexpr int K = 8; CALL; } break;     \
+    default: return NWX_E_INVALID;                    \
+  }
+
+extern "C" int nwx_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                 const float* noise, int64_t N, int S, int white_bkgd, float* rgb,
+                                 float* disp, float* acc, float* depth, float* weights, int32_t* flags,
+                                 void* stream) {
+  NWX_REQUIRE(raw && z && rays_d && rgb && d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
+  if (N == 0) return NWX_OK;
+  auto st = (cudaStream_t)stream;
+  NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
+                        raw, z, rays_d, d_stride, noise, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags)));
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+extern "C" int nwx_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                 const float* noise, const float* weights, const float* d_rgb, int64_t N,
+                                 int S, int white_bkgd, float* d_raw, void* stream) {
+  (void)weights;   // recomputed from raw: cheaper than re-reading 4 B/sample and exact for alpha = 0
+  NWX_REQUIRE(raw && z && rays_d && d_rgb && d_raw && d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
+  if (N == 0) return NWX_OK;
+  auto st = (cudaStream_t)stream;
+  NWX_DISPATCH_K(S, (nwx::composite_bwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
+                        raw, z, rays_d, d_stride, noise, d_rgb, N, S, white_bkgd, d_raw)));
+  NWX_LAUNCHED();
+  return NWX_OK;
+}

@@ -1,0 +1,218 @@
+// Context (packed weights + scratch) and the fused launch sequence of _volumetric_rendering
+// (reference nerf/inference/nerf_replica_inference_handler.py:203-277 and
+// nerf/training/nerf_replica_training_handler.py:534-618).
+//
+// The reference walks a frame in 38 Python ray chunks x 64 network chunks, with 22 host syncs
+// per chunk.  Here one chunk of any size is 7 kernel launches on one
+// stream, no host synchronisation, nothing per-point materialised except raw [N,S,4]:
+//   coarse_z -> dirbias(coarse) -> MLP(coarse) -> composite -> sample_pdf+merge
+//            -> dirbias(fine)   -> MLP(fine)   -> composite (+ to8b)
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mlp.cuh"
+
+std::atomic<int64_t> g_nwx_launches{0};
+
+struct nwx_ctx {
+  int device = 0;
+  nwx::PackedNet net[2];
+  int mlp_variant = 0;
+  // scratch, grown on demand (nwx_ctx_reserve pre-sizes it)
+  float* scratch = nullptr;
+  size_t scratch_floats = 0;
+  float* dbg_out = nullptr;      // optional tap target set by nwx_debug_tap
+  int dbg_layer = -1;
+  uint32_t* diag = nullptr;      // optional host-mapped diagnostics
+};
+
+namespace {
+
+struct ScratchPlan {
+  size_t z_c, raw_c, w_c, z_s, z_f, raw_f, dirbias, rgb_c, rgb_f, total;
+};
+
+ScratchPlan plan_scratch(int64_t N, int Sc, int Ni) {
+  ScratchPlan p{};
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) & ~(size_t)63; return o; };   // 256 B aligned
+  const int Sf = Sc + Ni;
+  p.z_c = take((size_t)N * Sc);
+  p.raw_c = take((size_t)N * Sc * 4);
+  p.w_c = take((size_t)N * Sc);
+  p.z_s = take((size_t)N * Ni);
+  p.z_f = take((size_t)N * Sf);
+  p.raw_f = take((size_t)N * Sf * 4);
+  p.dirbias = take((size_t)N * nwx::kViewHidden);
+  p.rgb_c = take((size_t)N * 3);
+  p.rgb_f = take((size_t)N * 3);
+  p.total = off;
+  return p;
+}
+
+int ensure_scratch(nwx_ctx* ctx, size_t floats) {
+  if (floats <= ctx->scratch_floats) return NWX_OK;
+  if (ctx->scratch) NWX_CUDA_TRY(cudaFree(ctx->scratch));
+  ctx->scratch = nullptr;
+  ctx->scratch_floats = 0;
+  NWX_CUDA_TRY(cudaMalloc(&ctx->scratch, floats * sizeof(float)));
+  ctx->scratch_floats = floats;
+  return NWX_OK;
+}
+
+}  // namespace
+
+extern "C" int nwx_version(void) { return NWX_VERSION; }
+
+extern "C" const char* nwx_error_string(int code) {
+  switch (code) {
+    case NWX_OK: return "ok";
+    case NWX_E_INVALID: return "invalid argument";
+    case NWX_E_NO_WEIGHTS: return "weights not loaded (call nwx_load_weights)";
+    case NWX_E_UNSUPPORTED: return "device is not sm_100 (B200); there is no fallback path";
+    default:
+      if (code >= NWX_E_CUDA) return cudaGetErrorString((cudaError_t)(code - NWX_E_CUDA));
+      return "unknown error";
+  }
+}
+
+extern "C" int64_t nwx_launch_count(void) { return g_nwx_launches.load(std::memory_order_relaxed); }
+
+extern "C" int nwx_ctx_create(int device, nwx_ctx** out) {
+  NWX_REQUIRE(out);
+  *out = nullptr;
+  NWX_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NWX_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return NWX_E_UNSUPPORTED;     // tcgen05/TMEM only; the product has no fallback
+  nwx_ctx* c = new (std::nothrow) nwx_ctx();
+  if (!c) return NWX_E_INVALID;
+  c->device = device;
+  *out = c;
+  return NWX_OK;
+}
+
+extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
+  if (!ctx) return NWX_OK;
+  cudaSetDevice(ctx->device);
+  for (auto& n : ctx->net) {
+    if (n.wimg) cudaFree(n.wimg);
+    if (n.wdir_t) cudaFree(n.wdir_t);
+    if (n.bview) cudaFree(n.bview);
+  }
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  delete ctx;
+  return NWX_OK;
+}
+
+extern "C" int nwx_load_weights(nwx_ctx* ctx, int which, const float* const* tensors, void* stream) {
+  NWX_REQUIRE(ctx && tensors && (which == NWX_NET_COARSE || which == NWX_NET_FINE));
+  for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) NWX_REQUIRE(tensors[i] != nullptr);
+  return nwx::pack_network(ctx->net[which], tensors, (cudaStream_t)stream);
+}
+
+extern "C" int nwx_set_mlp_variant(nwx_ctx* ctx, int variant) {
+  NWX_REQUIRE(ctx && variant >= 0 && variant <= 3);
+  ctx->mlp_variant = variant;
+  return NWX_OK;
+}
+
+// Test/diagnostic hooks (declared here, not part of the reference-facing surface in nwx.h).
+extern "C" int nwx_debug_tap(nwx_ctx* ctx, int layer, float* out) {
+  NWX_REQUIRE(ctx);
+  ctx->dbg_layer = layer;
+  ctx->dbg_out = out;
+  return NWX_OK;
+}
+extern "C" int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped) {
+  NWX_REQUIRE(ctx);
+  ctx->diag = host_mapped;
+  return NWX_OK;
+}
+
+extern "C" int nwx_ctx_reserve(nwx_ctx* ctx, int64_t max_rays, int n_samples, int n_importance) {
+  NWX_REQUIRE(ctx && max_rays > 0 && n_samples > 0 && n_importance >= 0);
+  return ensure_scratch(ctx, plan_scratch(max_rays, n_samples, n_importance).total);
+}
+
+static int run_mlp(nwx_ctx* ctx, int which, const float* rays, int ray_dim, const float* z, const float* pts,
+                   const float* dirs, int dir_stride, int64_t n_dir, int64_t P, int S, float* dirbias,
+                   float* raw_out, cudaStream_t st, const float* embedded = nullptr) {
+  const nwx::PackedNet& net = ctx->net[which];
+  if (!net.loaded) return NWX_E_NO_WEIGHTS;
+  int rc = nwx::launch_dirbias(net, dirs, dir_stride, n_dir, embedded != nullptr, dirbias, st);
+  if (rc) return rc;
+  nwx::MlpArgs a{};
+  a.rays = rays; a.z = z; a.pts = pts; a.embedded = embedded; a.wimg = net.wimg; a.dirbias = dirbias; a.raw_out = raw_out;
+  a.dbg_out = ctx->dbg_out; a.dbg_layer = ctx->dbg_layer; a.diag = ctx->diag;
+  a.P = P; a.ray_dim = ray_dim; a.S = S;
+  return nwx::launch_mlp(net, a, ctx->mlp_variant, st);
+}
+
+extern "C" int nwx_mlp_forward(nwx_ctx* ctx, int which, const float* rays, int ray_dim, const float* z,
+                               int64_t N, int S, float* raw_out, void* stream) {
+  NWX_REQUIRE(ctx && rays && z && raw_out && (which == 0 || which == 1) && ray_dim >= NWX_RAY_DIM && S >= 1 && N >= 0);
+  if (N == 0) return NWX_OK;
+  int rc = ensure_scratch(ctx, (size_t)N * nwx::kViewHidden);
+  if (rc) return rc;
+  return run_mlp(ctx, which, rays, ray_dim, z, nullptr, rays + 8, ray_dim, N, N * S, S, ctx->scratch, raw_out,
+                 (cudaStream_t)stream);
+}
+
+extern "C" int nwx_mlp_forward_points(nwx_ctx* ctx, int which, const float* pts, const float* dirs, int64_t P,
+                                      int pts_per_dir, float* raw_out, void* stream) {
+  NWX_REQUIRE(ctx && pts && dirs && raw_out && (which == 0 || which == 1) && P >= 0 && pts_per_dir >= 1);
+  if (P == 0) return NWX_OK;
+  const int64_t n_dir = (P + pts_per_dir - 1) / pts_per_dir;
+  int rc = ensure_scratch(ctx, (size_t)n_dir * nwx::kViewHidden);
+  if (rc) return rc;
+  return run_mlp(ctx, which, nullptr, 0, nullptr, pts, dirs, 3, n_dir, P, pts_per_dir, ctx->scratch, raw_out,
+                 (cudaStream_t)stream);
+}
+
+extern "C" int nwx_mlp_forward_embedded(nwx_ctx* ctx, int which, const float* x, int64_t P, float* raw_out,
+                                        void* stream) {
+  NWX_REQUIRE(ctx && x && raw_out && (which == 0 || which == 1) && P >= 0);
+  if (P == 0) return NWX_OK;
+  int rc = ensure_scratch(ctx, (size_t)P * nwx::kViewHidden);
+  if (rc) return rc;
+  return run_mlp(ctx, which, nullptr, 0, nullptr, nullptr, x + nwx::kPeXyz, nwx::kPeXyz + nwx::kPeDir, P, P, 1,
+                 ctx->scratch, raw_out, (cudaStream_t)stream, x);
+}
+
+extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const nwx_render_opts* o,
+                               const nwx_render_out* out, void* stream) {
+  NWX_REQUIRE(ctx && rays && o && out && out->rgb_fine && N >= 0);
+  NWX_REQUIRE(o->n_samples >= 11 && o->n_samples <= 128 && o->n_importance >= 1 && o->n_importance <= 128);
+  NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin));
+  if (N == 0) return NWX_OK;
+  if (!ctx->net[0].loaded || !ctx->net[1].loaded) return NWX_E_NO_WEIGHTS;
+  auto st = (cudaStream_t)stream;
+  const int Sc = o->n_samples, Ni = o->n_importance, Sf = Sc + Ni, rd = o->ray_dim;
+  const ScratchPlan pl = plan_scratch(N, Sc, Ni);
+  int rc = ensure_scratch(ctx, pl.total);
+  if (rc) return rc;
+  float* s = ctx->scratch;
+  // caller-provided outputs double as the working buffers where they exist
+  float* z_c = out->z_vals_coarse ? out->z_vals_coarse : s + pl.z_c;
+  float* raw_c = out->raw_coarse ? out->raw_coarse : s + pl.raw_c;
+  float* w_c = out->weights_coarse ? out->weights_coarse : s + pl.w_c;
+  float* z_s = out->z_samples ? out->z_samples : s + pl.z_s;
+  float* z_f = out->z_vals_fine ? out->z_vals_fine : s + pl.z_f;
+  float* raw_f = out->raw_fine ? out->raw_fine : s + pl.raw_f;
+  float* rgb_c = out->rgb_coarse ? out->rgb_coarse : s + pl.rgb_c;
+  float* dirb = s + pl.dirbias;
+  if (out->flags) NWX_CUDA_TRY(cudaMemsetAsync(out->flags, 0, sizeof(int32_t), st));
+
+  if ((rc = nwx_coarse_z(rays, rd, N, Sc, o->t_vals, o->t_rand, z_c, st))) return rc;
+  if ((rc = run_mlp(ctx, NWX_NET_COARSE, rays, rd, z_c, nullptr, rays + 8, rd, N, N * Sc, Sc, dirb, raw_c, st))) return rc;
+  if ((rc = nwx_composite_fwd(raw_c, z_c, rays + 3, rd, o->noise_coarse, N, Sc, o->white_bkgd, rgb_c, out->disp_coarse,
+                              out->acc_coarse, out->depth_coarse, w_c, out->flags, st))) return rc;
+  if ((rc = nwx_sample_pdf(z_c, w_c, Sc, o->u, o->u_lin, Ni, N, z_s, z_f, out->inds, out->z_std, st))) return rc;
+  if ((rc = run_mlp(ctx, NWX_NET_FINE, rays, rd, z_f, nullptr, rays + 8, rd, N, N * Sf, Sf, dirb, raw_f, st))) return rc;
+  if ((rc = nwx_composite_fwd(raw_f, z_f, rays + 3, rd, o->noise_fine, N, Sf, o->white_bkgd, out->rgb_fine, out->disp_fine,
+                              out->acc_fine, out->depth_fine, out->weights_fine, out->flags, st))) return rc;
+  if (out->rgb8_fine && (rc = nwx_to8b(out->rgb_fine, N * 3, out->rgb8_fine, st))) return rc;
+  return NWX_OK;
+}

@@ -1,0 +1,560 @@
+// K3: fused positional encoding + 8x256 NeRF MLP on tcgen05 tensor cores.
+//
+// Replaces, in ONE persistent kernel, the whole of run_network (reference
+// nerf/models/model_utils.py:13-30): pts = o + d*z, Embedding.embed of points (embedding.py:44-48),
+// the per-point view-direction broadcast, batchify (utils/batch_utils.py:28-39) and
+// NeRFModel.forward (nerf_model.py:45-83).  Nothing per-point is materialised in HBM: in = 4 B
+// (z) per point, out = 16 B (raw rgb+sigma).
+//
+// Organisation (one CTA, or a CTA pair, per SM; 16 warps):
+//   warp 0      TMA producer  : streams pre-swizzled bf16 weight K-blocks L2 -> smem ring
+//                               (cp.async.bulk + mbarrier complete_tx)
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma (M=128|256, N=256|128, K=16),
+//                               accumulators in TMEM; tcgen05.commit signals mbarriers
+//   warp 2      TMEM allocator
+//   warps 4-7   PE producers  : thread = point; position, 63 sin/cos features -> bf16, written
+//                               straight into the swizzled A-operand tile in smem
+//   warps 8-15  epilogue      : tcgen05.ld accumulator -> +bias, ReLU -> bf16 -> next layer's
+//                               A-operand tile in smem (in place); fp32 sigma and rgb heads
+// Two 128-point tiles are in flight per CTA (TMEM: 2 x 256 fp32 columns): while the tensor core
+// runs layer l of tile B the epilogue warps drain layer l of tile A, so the tensor pipe only
+// idles when an epilogue is slower than an MMA layer.
+//
+// Variants (template): kPair = cta_group::2 (CTA pair shares each weight K-block: CTA r holds
+// output rows [r*N/2, (r+1)*N/2) of B, UMMA M = 256), kResident = a weight K-block stays in
+// smem for both in-flight tiles (halves L2->smem traffic).  See DESIGN.md for the roofline.
+//
+// Numerics: bf16 operands (PE features, weights, hidden activations), fp32 accumulation and
+// biases; the sigma head, the 27-d view-direction term of the views layer and the rgb head are
+// evaluated in fp32 on CUDA cores (oracle model: mlp_forward_bf16_emul).
+#include "mlp.cuh"
+#include "sm100_ptx.cuh"
+
+namespace nwx {
+
+using namespace ptx;
+
+constexpr int kTileM = 128;                     // points per tile (= TMEM lanes)
+constexpr int kThreads = 512;
+constexpr int kHBytes = kTileM * kHidden * 2;   // 65536: one activation tile, 4 K-blocks of 16 KB
+constexpr int kABlock = kTileM * 64 * 2;        // 16384: one [128 x 64] bf16 K-block of A
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+// chunk schedule: layer 5 is split so that a chunk never needs more than 4 resident K-blocks
+constexpr int kNumChunks = 11;
+__device__ __forceinline__ int chunk_layer(int c) { return c <= 5 ? c : c - 1; }
+__device__ __forceinline__ int chunk_kb0(int c) { return c == 6 ? 1 : 0; }
+__device__ __forceinline__ int chunk_nkb(int c) { return (c == 0 || c == 5) ? 1 : 4; }
+__device__ __forceinline__ int layer_gkb0(int l) {     // global K-block index of a layer's first K-block
+  return l == 0 ? 0 : (l <= 5 ? 1 + 4 * (l - 1) : 22 + 4 * (l - 6));
+}
+
+template <bool kPair, int kStages>
+struct SmemLayout {
+  static constexpr uint32_t kStageBytes = kPair ? kKBlockBytes / 2 : kKBlockBytes;
+  static constexpr uint32_t h0 = 0;
+  static constexpr uint32_t pe0 = 2 * kHBytes;
+  static constexpr uint32_t w0 = pe0 + 2 * kABlock;
+  static constexpr uint32_t bar0 = w0 + kStages * kStageBytes;
+  // barrier slots (8 B each)
+  static constexpr uint32_t w_full = bar0;
+  static constexpr uint32_t w_empty = w_full + 8 * kStages;
+  static constexpr uint32_t w_peer = w_empty + 8 * kStages;
+  static constexpr uint32_t acc_full = w_peer + 8 * kStages;
+  static constexpr uint32_t a_ready = acc_full + 16;
+  static constexpr uint32_t pe_ready = a_ready + 16;
+  static constexpr uint32_t pe_free = pe_ready + 16;
+  static constexpr uint32_t tmem_slot = pe_free + 16;
+  static constexpr uint32_t total = tmem_slot + 16;
+  static constexpr uint32_t alloc_bytes = total + 1024;   // slack for manual 1024 B alignment
+};
+
+struct WaitCtx {
+  uint32_t* diag;
+  uint32_t code;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) {                  // never hang the GPU: report and abort the grid
+      if (w.diag) {
+        w.diag[0] = 0xDEAD0000u | w.code;
+        w.diag[1] = blockIdx.x;
+        w.diag[2] = bar;
+        w.diag[3] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+// 63 positional-encoding features of one point (+1 zero pad) as 32 packed bf16 pairs.
+// Column order of Embedding.embed (embedding.py:31-38,48): x/s, then per k: sin(x/s*2^k)(3), cos(..)(3).
+__device__ __forceinline__ void encode_point(float px, float py, float pz, uint32_t (&pk)[32]) {
+  float f[64];
+  const float x[3] = {__fdiv_rn(px, 10.0f), __fdiv_rn(py, 10.0f), __fdiv_rn(pz, 10.0f)};   // scalar_factor 10
+  f[0] = x[0]; f[1] = x[1]; f[2] = x[2];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const float sc = (float)(1 << k);            // exact power of two: x*2^k is exact
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s, c;
+      sincosf(x[a] * sc, &s, &c);
+      f[3 + 6 * k + a] = s;
+      f[3 + 6 * k + 3 + a] = c;
+    }
+  }
+  f[63] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+}
+
+enum { kEpiRelu = 0, kEpiReluSigma = 1, kEpiLinear = 2 };
+
+// Hidden-layer epilogue of one thread (= one point / TMEM lane) over its 128-column half:
+// accumulator -> +bias -> (ReLU) -> bf16 -> the next layer's swizzled A-operand tile.
+// Returns this half's partial of the fp32 sigma head when kMode == kEpiReluSigma.
+template <int kMode, bool kTap>
+__device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, uint32_t d_tmem, uint32_t hrow,
+                                                 int row, int wg, float* tap_row) {
+  float sig = 0.f;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    const int col = wg * 128 + cc * 32;
+    uint32_t v[32];
+    tmem_ld32(d_tmem + col, v);
+    tmem_wait_ld();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float a = __uint_as_float(v[j]) + cst.bias[l][col + j];
+      const float b = __uint_as_float(v[j + 1]) + cst.bias[l][col + j + 1];
+      if (kMode == kEpiReluSigma) {                  // sigma head on fp32 relu(h7), nerf_model.py:63
+        sig = fmaf(fmaxf(a, 0.f), cst.w_alpha[col + j], sig);
+        sig = fmaf(fmaxf(b, 0.f), cst.w_alpha[col + j + 1], sig);
+      }
+      if (kTap && tap_row) {
+        tap_row[col + j] = kMode == kEpiLinear ? a : fmaxf(a, 0.f);
+        tap_row[col + j + 1] = kMode == kEpiLinear ? b : fmaxf(b, 0.f);
+      }
+      pk[j >> 1] = (kMode == kEpiLinear) ? pack_bf16x2(a, b) : pack_bf16x2_relu(a, b);   // feature: no ReLU (:64)
+    }
+    const uint32_t kbase = hrow + (col >> 6) * kABlock;
+    const int j0 = (col & 63) >> 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+  return sig;
+}
+
+template <bool kPair, bool kResident, int kStages, bool kTap>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst) {
+  using L = SmemLayout<kPair, kStages>;
+  constexpr int kCG = kPair ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0;
+  const int units = kPair ? gridDim.x / 2 : gridDim.x;
+  const int unit = kPair ? blockIdx.x / 2 : blockIdx.x;
+  const int64_t P = args.P;
+  const int iters = args.iters;
+  auto tile_of = [&](int it, int t) -> int64_t {
+    const int64_t u = ((int64_t)it * units + unit) * 2 + t;
+    return kPair ? u * 2 + rank : u;
+  };
+  // barriers that the MMA issuer waits on live in the leader CTA (rank 0)
+  auto leader = [&](uint32_t local) -> uint32_t { return kPair ? mapa(local, 0) : local; };
+
+  // ------------------------------------------------------------------ setup ----
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(sbase + L::w_full + 8 * s, 1);
+      mbar_init(sbase + L::w_empty + 8 * s, 1);
+      mbar_init(sbase + L::w_peer + 8 * s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(sbase + L::acc_full + 8 * t, 1);
+      mbar_init(sbase + L::a_ready + 8 * t, 8 * kCG);     // one arrive per epilogue warp (per CTA)
+      mbar_init(sbase + L::pe_ready + 8 * t, 4 * kCG);    // one arrive per PE warp (per CTA)
+      mbar_init(sbase + L::pe_free + 8 * t, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kCG>(sbase + L::tmem_slot, 512);
+  tc_fence_before();
+  if (kPair) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + L::tmem_slot);
+
+  if (warp == 0) {
+    // =========================================================== TMA producer ====
+    if (lane == 0) {
+      const WaitCtx wc{args.diag, 0x100u};
+      uint32_t fill = 0;
+      for (int it = 0; it < iters; ++it) {
+        for (int c = 0; c < kNumChunks; ++c) {
+          const int l = chunk_layer(c);
+          const uint32_t bytes = (l == 9 ? kKBlockBytes / 2 : kKBlockBytes) / kCG;
+          for (int t = 0; t < (kResident ? 1 : 2); ++t) {
+            for (int kb = 0; kb < chunk_nkb(c); ++kb, ++fill) {
+              const uint32_t stage = fill % kStages, round = fill / kStages;
+              mbar_wait(sbase + L::w_empty + 8 * stage, (round & 1) ^ 1, wc);
+              const uint32_t bar = sbase + L::w_full + 8 * stage;
+              mbar_arrive_expect_tx(bar, bytes);
+              const uint8_t* src = args.wimg + kblock_offset(layer_gkb0(l) + chunk_kb0(c) + kb) + rank * bytes;
+              bulk_g2s(sbase + L::w0 + stage * L::kStageBytes, src, bytes, bar);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================= MMA issuer ====
+    if (lane == 0) {
+      const WaitCtx wc{args.diag, 0x200u};
+      uint32_t fill = 0;
+      if (rank == 0) {
+        for (int it = 0; it < iters; ++it) {
+          for (int c = 0; c < kNumChunks; ++c) {
+            const int l = chunk_layer(c);
+            const int nkb = chunk_nkb(c);
+            const bool first_chunk = (c != 6), last_chunk = (c != 5);
+            const uint32_t idesc = umma_idesc_bf16(kTileM * kCG, l == 9 ? kViewHidden : kHidden);
+            for (int t = 0; t < 2; ++t) {
+              if (first_chunk) {
+                if (l == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
+                // a_ready[t] completes once per layer epilogue: phase index = 10*it + l - 1
+                if (l != 0 || it != 0) mbar_wait(sbase + L::a_ready + 8 * t, (l + 1) & 1, wc);
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + t * kHidden;
+              for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t f = kResident ? fill + kb : fill++;
+                const uint32_t stage = f % kStages, round = f / kStages;
+                if (!kResident || t == 0) {
+                  mbar_wait(sbase + L::w_full + 8 * stage, round & 1, wc);
+                  if (kPair) mbar_wait(sbase + L::w_peer + 8 * stage, round & 1, wc);
+                  tc_fence_after();
+                }
+                const int akb = chunk_kb0(c) + kb;          // K-block index within the layer
+                uint32_t a_addr;
+                if (l == 0 || (l == 5 && akb == 0)) a_addr = sbase + L::pe0 + t * kABlock;
+                else a_addr = sbase + L::h0 + t * kHBytes + (l == 5 ? akb - 1 : akb) * kABlock;
+                const uint64_t adesc = umma_desc_k_sw128(a_addr);
+                const uint64_t bdesc = umma_desc_k_sw128(sbase + L::w0 + stage * L::kStageBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                 // 4 x (K = 16) per 64-wide K-block: +32 B
+                  umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (akb | k) != 0);
+                if (!kResident || t == 1) umma_commit<kCG>(sbase + L::w_empty + 8 * stage);
+              }
+              if (last_chunk) umma_commit<kCG>(sbase + L::acc_full + 8 * t);
+              if (c == 5) umma_commit<kCG>(sbase + L::pe_free + 8 * t);
+            }
+            if (kResident) fill += nkb;
+          }
+        }
+      } else {
+        // peer CTA of a pair: relay "my half of the weight K-block has landed" to the leader
+        const uint32_t per_iter = kResident ? kNumKBlocks : 2 * kNumKBlocks;
+        for (uint32_t n = 0; n < per_iter * (uint32_t)iters; ++n, ++fill) {
+          const uint32_t stage = fill % kStages, round = fill / kStages;
+          mbar_wait(sbase + L::w_full + 8 * stage, round & 1, wc);
+          mbar_arrive_cluster(mapa(sbase + L::w_peer + 8 * stage, 0));
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================================================ PE producers ====
+    const WaitCtx wc{args.diag, 0x300u};
+    const int row = (warp - 4) * 32 + lane;
+    for (int it = 0; it < iters; ++it) {
+      for (int t = 0; t < 2; ++t) {
+        int64_t p = tile_of(it, t) * kTileM + row;
+        if (p >= P) p = P - 1;                                  // tail tile: recompute a valid point
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (args.embedded) {
+          // handled below: features are read, not computed
+        } else if (args.pts) {
+          px = __ldg(args.pts + p * 3 + 0); py = __ldg(args.pts + p * 3 + 1); pz = __ldg(args.pts + p * 3 + 2);
+        } else {
+          const int64_t ray = p / args.S;
+          const float* r = args.rays + ray * args.ray_dim;
+          const float zz = __ldg(args.z + p);
+          px = __fadd_rn(__ldg(r + 0), __fmul_rn(__ldg(r + 3), zz));   // inference handler:223
+          py = __fadd_rn(__ldg(r + 1), __fmul_rn(__ldg(r + 4), zz));
+          pz = __fadd_rn(__ldg(r + 2), __fmul_rn(__ldg(r + 5), zz));
+        }
+        uint32_t pk[32];
+        if (args.embedded) {
+          const float* e = args.embedded + p * (kPeXyz + kPeDir);
+#pragma unroll
+          for (int i = 0; i < 31; ++i) pk[i] = pack_bf16x2(__ldg(e + 2 * i), __ldg(e + 2 * i + 1));
+          pk[31] = pack_bf16x2(__ldg(e + 62), 0.0f);
+        } else {
+          encode_point(px, py, pz, pk);
+        }
+        if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
+        const uint32_t dst = sbase + L::pe0 + t * kABlock + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(dst + ((j ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(leader(sbase + L::pe_ready + 8 * t));
+          else mbar_arrive(sbase + L::pe_ready + 8 * t);
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================================================ epilogue ====
+    const WaitCtx wc{args.diag, 0x400u};
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int wg = (warp - 8) >> 2;               // column half
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float sig0 = 0.f, sig1 = 0.f;                 // sigma-head partials of tile 0 / tile 1
+    for (int it = 0; it < iters; ++it) {
+      for (int l = 0; l < kNumLayers; ++l) {
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(sbase + L::acc_full + 8 * t, l & 1, wc);   // phase index = 10*it + l
+          tc_fence_after();
+          const uint32_t d_tmem = lane_addr + t * kHidden;
+          const int64_t p = tile_of(it, t) * kTileM + row;
+          float* tap_row = nullptr;
+          if (kTap && args.dbg_out != nullptr && args.dbg_layer == l && p < P) tap_row = args.dbg_out + p * kHidden;
+          if (l < 9) {
+            const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
+            if (l == 7) {
+              const float sig = epilogue_hidden<kEpiReluSigma, kTap>(cst, l, d_tmem, hrow, row, wg, tap_row);
+              if (t == 0) sig0 = sig; else sig1 = sig;
+            } else if (l == 8) {
+              epilogue_hidden<kEpiLinear, kTap>(cst, l, d_tmem, hrow, row, wg, tap_row);
+            } else {
+              epilogue_hidden<kEpiRelu, kTap>(cst, l, d_tmem, hrow, row, wg, tap_row);
+            }
+            fence_proxy_async_smem();            // my smem writes -> visible to the next layer's UMMA
+          } else {
+            // views layer (N = 128): + (b_view + W_view[:,256:] . pe(dir)), ReLU, fp32 rgb head
+            const int64_t pc = p < P ? p : P - 1;
+            const float* db = args.dirbias + (pc / args.S) * kViewHidden;
+            float r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              const int col = wg * 64 + cc * 32;
+              uint32_t v[32];
+              tmem_ld32(d_tmem + col, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + col + j));
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float hv = fmaxf(__uint_as_float(v[j + q]) + dd[q], 0.f);       // nerf_model.py:68-70
+                  if (kTap && tap_row) tap_row[col + j + q] = hv;
+                  r = fmaf(hv, cst.w_rgb[0][col + j + q], r);                            // :74
+                  g = fmaf(hv, cst.w_rgb[1][col + j + q], g);
+                  b = fmaf(hv, cst.w_rgb[2][col + j + q], b);
+                }
+              }
+            }
+            // combine the two column halves through the (now dead) activation tile, then store
+            float4* scratch = reinterpret_cast<float4*>(sgen + L::h0 + t * kHBytes);
+            const float sig = t == 0 ? sig0 : sig1;
+            if (wg == 1) scratch[row] = make_float4(r, g, b, sig);
+            named_bar_sync(1, 256);
+            if (wg == 0 && p < P) {
+              const float4 o = scratch[row];
+              float4 out;
+              out.x = r + o.x + cst.b_rgb[0];
+              out.y = g + o.y + cst.b_rgb[1];
+              out.z = b + o.z + cst.b_rgb[2];
+              out.w = sig + o.w + cst.b_alpha;
+              reinterpret_cast<float4*>(args.raw_out)[p] = out;                        // (rgb, sigma), :76
+            }
+          }
+          tc_fence_before();                     // my tcgen05.ld's are complete before the MMA overwrites D
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
+            else mbar_arrive(sbase + L::a_ready + 8 * t);
+          }
+        }
+      }
+    }
+  }
+
+  // --------------------------------------------------------------- teardown ----
+  tc_fence_before();
+  if (kPair) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCG>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 nn.Linear weights [out, in] -> bf16 K-block images in the exact byte
+// layout the UMMA B descriptor expects (K-major, SWIZZLE_128B: row n at n*128 B, 16-byte chunk c
+// of the row stored at chunk position c ^ (n & 7)), so the kernel moves them with flat bulk copies.
+// ------------------------------------------------------------------------------------------------
+struct PackSrc {
+  const float* w[kNumLayers];     // pts 0..7, feature, views
+};
+
+__global__ void pack_weights_kernel(PackSrc src, uint8_t* __restrict__ wimg) {
+  const int g = blockIdx.x;                       // global K-block
+  int l = 0, kb = g;
+  while (kb >= layer_kblocks(l)) { kb -= layer_kblocks(l); ++l; }
+  const int rows = (l == 9) ? kViewHidden : kHidden;
+  const int in_dim = (l == 0) ? kPeXyz : (l == 5 ? kPeXyz + kHidden : (l == 9 ? kHidden + kPeDir : kHidden));
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(wimg + kblock_offset(g));
+  for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
+    const int n = e >> 6, c = e & 63;
+    int k;                                        // source input column, -1 = zero padding
+    if (l == 0) k = (c < kPeXyz) ? c : -1;
+    else if (l == 5) k = (kb == 0) ? ((c < kPeXyz) ? c : -1) : kPeXyz + (kb - 1) * 64 + c;   // [pe | h], nerf_model.py:59
+    else k = kb * 64 + c;                         // views: only the 256 feature columns (:66)
+    const float v = (k >= 0) ? src.w[l][(size_t)n * in_dim + k] : 0.0f;
+    const int chunk = (c >> 3) ^ (n & 7);
+    img[n * 64 + chunk * 8 + (c & 7)] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void pack_dir_kernel(const float* __restrict__ wv, float* __restrict__ wdir_t) {
+  // wdir_t[i][j] = W_view[j][256 + i]
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPeDir * kViewHidden; e += gridDim.x * blockDim.x) {
+    const int i = e / kViewHidden, j = e - i * kViewHidden;
+    wdir_t[e] = wv[(size_t)j * (kHidden + kPeDir) + kHidden + i];
+  }
+}
+
+int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
+  // state_dict order: pts.{0..7}.{w,b} (0..15), views.{w,b} (16,17), feature (18,19), alpha (20,21), rgb (22,23)
+  if (!net.wimg) NWX_CUDA_TRY(cudaMalloc(&net.wimg, kWeightImageBytes));
+  if (!net.wdir_t) NWX_CUDA_TRY(cudaMalloc(&net.wdir_t, sizeof(float) * kPeDir * kViewHidden));
+  if (!net.bview) NWX_CUDA_TRY(cudaMalloc(&net.bview, sizeof(float) * kViewHidden));
+  PackSrc src;
+  for (int i = 0; i < 8; ++i) src.w[i] = t[2 * i];
+  src.w[8] = t[18];
+  src.w[9] = t[16];
+  pack_weights_kernel<<<kNumKBlocks, 256, 0, st>>>(src, net.wimg);
+  NWX_LAUNCHED();
+  pack_dir_kernel<<<4, 256, 0, st>>>(t[16], net.wdir_t);
+  NWX_LAUNCHED();
+  NWX_CUDA_TRY(cudaMemcpyAsync(net.bview, t[17], sizeof(float) * kViewHidden, cudaMemcpyDeviceToDevice, st));
+  MlpConsts& c = net.consts;
+  for (int i = 0; i < 8; ++i)
+    NWX_CUDA_TRY(cudaMemcpyAsync(c.bias[i], t[2 * i + 1], sizeof(float) * kHidden, cudaMemcpyDeviceToHost, st));
+  NWX_CUDA_TRY(cudaMemcpyAsync(c.bias[8], t[19], sizeof(float) * kHidden, cudaMemcpyDeviceToHost, st));
+  NWX_CUDA_TRY(cudaMemcpyAsync(c.w_alpha, t[20], sizeof(float) * kHidden, cudaMemcpyDeviceToHost, st));
+  NWX_CUDA_TRY(cudaMemcpyAsync(&c.b_alpha, t[21], sizeof(float), cudaMemcpyDeviceToHost, st));
+  NWX_CUDA_TRY(cudaMemcpyAsync(c.w_rgb, t[22], sizeof(float) * 3 * kViewHidden, cudaMemcpyDeviceToHost, st));
+  NWX_CUDA_TRY(cudaMemcpyAsync(c.b_rgb, t[23], sizeof(float) * 3, cudaMemcpyDeviceToHost, st));
+  NWX_CUDA_TRY(cudaStreamSynchronize(st));       // load-time only: the consts are a host-side launch argument
+  net.loaded = true;
+  return NWX_OK;
+}
+
+// dirbias[n][j] = b_view[j] + sum_i W_view[j][256+i] * pe_dir(dir_n)[i]   (fp32)
+// pe_dir = Embedding(num_freqs=4, scalar_factor=1).embed  (embedding.py:44-48)
+__global__ void __launch_bounds__(kViewHidden)
+dirbias_kernel(const float* __restrict__ dirs, int stride, int64_t n, int pre_embedded,
+               const float* __restrict__ wdir_t, const float* __restrict__ bview, float* __restrict__ out) {
+  constexpr int kRays = 8;
+  __shared__ float pe[kRays][kPeDir + 1];
+  const int64_t base = (int64_t)blockIdx.x * kRays;
+  for (int e = threadIdx.x; e < kRays * kPeDir; e += blockDim.x) {
+    const int r = e / kPeDir, i = e - r * kPeDir;
+    const int64_t ray = base + r < n ? base + r : n - 1;
+    float v;
+    if (pre_embedded || i < 3) v = __ldg(dirs + ray * stride + i);
+    else {
+      const int k = (i - 3) / 6, w = (i - 3) % 6, a = w % 3;
+      const float x = __ldg(dirs + ray * stride + a) * (float)(1 << k);
+      v = (w < 3) ? sinf(x) : cosf(x);
+    }
+    pe[r][i] = v;
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  float acc[kRays];
+  const float b = __ldg(bview + j);
+#pragma unroll
+  for (int r = 0; r < kRays; ++r) acc[r] = b;
+  for (int i = 0; i < kPeDir; ++i) {
+    const float w = __ldg(wdir_t + i * kViewHidden + j);
+#pragma unroll
+    for (int r = 0; r < kRays; ++r) acc[r] = fmaf(w, pe[r][i], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kRays; ++r)
+    if (base + r < n) out[(base + r) * kViewHidden + j] = acc[r];
+}
+
+int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, float* out,
+                   cudaStream_t st) {
+  if (n == 0) return NWX_OK;
+  dirbias_kernel<<<(unsigned)((n + 7) / 8), kViewHidden, 0, st>>>(dirs, stride, n, pre_embedded ? 1 : 0, net.wdir_t,
+                                                                 net.bview, out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+template <bool kPair, bool kResident, int kStages, bool kTap>
+static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
+  using Lay = SmemLayout<kPair, kStages>;
+  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap>;
+  static bool configured = false;
+  if (!configured) {
+    NWX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
+    configured = true;
+  }
+  const int64_t tiles = (args.P + kTileM - 1) / kTileM;
+  int ctas = num_sms();
+  if (kPair) ctas &= ~1;
+  const int units = kPair ? ctas / 2 : ctas;
+  const int tiles_per_unit_iter = kPair ? 4 : 2;
+  // do not launch more units than there is work for
+  int64_t need_units = (tiles + tiles_per_unit_iter - 1) / tiles_per_unit_iter;
+  int use_units = (int)(need_units < units ? need_units : units);
+  if (use_units < 1) use_units = 1;
+  args.iters = (int)((tiles + (int64_t)use_units * tiles_per_unit_iter - 1) / ((int64_t)use_units * tiles_per_unit_iter));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kPair ? use_units * 2 : use_units);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Lay::alloc_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NWX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args, net.consts));
+  g_nwx_launches.fetch_add(1, std::memory_order_relaxed);
+  return NWX_OK;
+}
+
+// variant: 0/1 = CTA pair + resident weights (production), 2 = CTA pair streaming,
+//          3 = single CTA streaming (cta_group::1)
+int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st) {
+  if (args.P <= 0) return NWX_OK;
+  const bool tap = args.dbg_out != nullptr;
+  switch (variant) {
+    case 0:
+    case 1: return tap ? launch_variant<true, true, 4, true>(net, args, st) : launch_variant<true, true, 4, false>(net, args, st);
+    case 2: return tap ? launch_variant<true, false, 4, true>(net, args, st) : launch_variant<true, false, 4, false>(net, args, st);
+    case 3: return tap ? launch_variant<false, false, 2, true>(net, args, st) : launch_variant<false, false, 2, false>(net, args, st);
+    default: return NWX_E_INVALID;
+  }
+}
+
+}  // namespace nwx

@@ -1,0 +1,66 @@
+// Shared helpers for libnwx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <atomic>
+
+#include "../../include/nwx.h"
+
+#define NWX_CUDA_TRY(expr)                                   \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return NWX_E_CUDA + (int)_e;      \
+  } while (0)
+
+#define NWX_REQUIRE(cond)                \
+  do {                                   \
+    if (!(cond)) return NWX_E_INVALID;   \
+  } while (0)
+
+extern std::atomic<int64_t> g_nwx_launches;   // defined in context.cu
+
+// Every kernel launch goes through this so bench.py can report gpu_launches.
+#define NWX_LAUNCHED()                                              \
+  do {                                                              \
+    g_nwx_launches.fetch_add(1, std::memory_order_relaxed);         \
+    cudaError_t _e = cudaGetLastError();                            \
+    if (_e != cudaSuccess) return NWX_E_CUDA + (int)_e;             \
+  } while (0)
+
+namespace nwx {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// Streaming (read-once) loads/stores that do not pollute L1.
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace nwx

@@ -1,0 +1,166 @@
+// K1: pinhole ray generation from c2w poses + coarse (stratified) depth sampling.
+//
+// Replaces create_rays / _get_rays_camera / _get_rays_world (reference nerf/rays/rays.py:6-71)
+// and the z_vals prologue of _volumetric_rendering (inference handler:216-220, training
+// handler:547-562).  HBM-streaming kernels: 44 B written per ray, 256 B per ray of z.
+//
+// Bit-exactness: every fp32 operation is issued in the order torch-CPU executes it, with
+// explicit round-to-nearest intrinsics so nvcc cannot contract mul+add into FMA where ATen
+// does not:
+//   d   = (R0*x + R1*y) + R2        -- ATen's small-matrix bmm loop, no FMA
+//   |d| = sqrt(fma(dz,dz, fma(dy,dy, dx*dx)))   -- ATen's vectorised norm reduction uses FMA
+// (both orders were determined against the reference's output, see DESIGN.md "bit-exact ops").
+#include "nwx_common.cuh"
+
+namespace nwx {
+
+constexpr int kRaygenThreads = 256;
+
+template <bool kViewDirs>
+__global__ void __launch_bounds__(kRaygenThreads)
+raygen_kernel(const float* __restrict__ c2w, int H, int W, float fx, float fy, float cx, float cy,
+              float near, float far, int64_t ray0, int64_t nrays, float* __restrict__ out) {
+  constexpr int kDim = kViewDirs ? 11 : 8;
+  __shared__ float tile[kRaygenThreads * kDim];
+  const int64_t base = (int64_t)blockIdx.x * kRaygenThreads;
+  const int64_t local = base + threadIdx.x;
+  if (local < nrays) {
+    const int64_t ray = ray0 + local;
+    const int64_t hw = (int64_t)H * W;
+    const int b = (int)(ray / hw);
+    const int pix = (int)(ray - (int64_t)b * hw);
+    const int row = pix / W, col = pix - row * W;
+    const float* T = c2w + (size_t)b * 16;
+    const float x = __fdiv_rn(__fsub_rn((float)col, cx), fx);   // rays.py:52
+    const float y = __fdiv_rn(__fsub_rn((float)row, cy), fy);   // rays.py:53
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)                                 // rays.py:67 (z component is 1)
+      d[k] = __fadd_rn(__fadd_rn(__fmul_rn(T[4 * k + 0], x), __fmul_rn(T[4 * k + 1], y)), T[4 * k + 2]);
+    float* r = tile + threadIdx.x * kDim;
+    r[0] = T[3]; r[1] = T[7]; r[2] = T[11];                     // rays.py:68
+    r[3] = d[0]; r[4] = d[1]; r[5] = d[2];
+    r[6] = near; r[7] = far;                                    // rays.py:26
+    if (kViewDirs) {
+      const float n = __fsqrt_rn(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
+      r[8] = __fdiv_rn(d[0], n); r[9] = __fdiv_rn(d[1], n); r[10] = __fdiv_rn(d[2], n);   // rays.py:24
+    }
+  }
+  __syncthreads();
+  // coalesced write-out of the block's contiguous [<=256, kDim] slab
+  const int64_t remaining = nrays - base;
+  const int count = (int)(remaining < kRaygenThreads ? remaining : kRaygenThreads) * kDim;
+  float* dst = out + base * kDim;
+  for (int i = threadIdx.x; i < count; i += kRaygenThreads) dst[i] = tile[i];
+}
+
+__global__ void __launch_bounds__(256)
+coarse_z_kernel(const float* __restrict__ rays, int ray_dim, int64_t total, int S,
+                const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                float* __restrict__ z_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / S;
+    const int s = (int)(i - n * S);
+    const float near = __ldg(rays + n * ray_dim + 6), far = __ldg(rays + n * ray_dim + 7);
+    auto zlin = [&](int k) {                                    // inference handler:218
+      const float t = __ldg(t_vals + k);
+      return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
+    };
+    float z = zlin(s);
+    if (t_rand != nullptr) {                                    // training handler:555-562
+      const float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zlin(s - 1)));
+      const float upper = (s == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zlin(s + 1), z));
+      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), ldg_stream(t_rand + i)));
+    }
+    z_out[i] = z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+to8b_kernel(const float* __restrict__ x, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // numpy: (255 * clip(x,0,1)).astype(uint8) -- fp32 multiply, truncation; NaN stays NaN -> 0
+    float v = x[i];
+    v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+    out[i] = (uint8_t)(int)__fmul_rn(255.0f, v);
+  }
+}
+
+// Embedding.embed (embedding.py:44-48) for callers that want the encoding materialised; the
+// render path never does (the MLP kernel generates the features in registers).
+__global__ void __launch_bounds__(256)
+embed_kernel(const float* __restrict__ x, int64_t P, int L, float scale, float* __restrict__ out) {
+  const int dim = 3 + 6 * L;
+  const int64_t total = P * dim, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t p = i / dim;
+    const int c = (int)(i - p * dim);
+    const int a = c < 3 ? c : (c - 3) % 3;
+    const float xs = __fdiv_rn(__ldg(x + p * 3 + a), scale);
+    float v = xs;
+    if (c >= 3) {
+      const int k = (c - 3) / 6;
+      const float arg = __fmul_rn(xs, exp2f((float)k));
+      v = ((c - 3) % 6 < 3) ? sinf(arg) : cosf(arg);
+    }
+    out[i] = v;
+  }
+}
+
+}  // namespace nwx
+
+extern "C" int nwx_embed(const float* x, int64_t P, int num_freqs, float scalar_factor, float* out, void* stream) {
+  NWX_REQUIRE(x && out && P >= 0 && num_freqs >= 0 && num_freqs <= 16 && scalar_factor != 0.0f);
+  if (P == 0) return NWX_OK;
+  int64_t blocks = (P * (3 + 6 * num_freqs) + 255) / 256;
+  const int64_t cap = (int64_t)nwx::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  nwx::embed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, P, num_freqs, scalar_factor, out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+extern "C" int nwx_raygen(const float* c2w, int B, int H, int W, float fx, float fy, float cx, float cy,
+                          float near, float far, int use_view_dirs, int64_t ray0, int64_t nrays,
+                          float* rays_out, void* stream) {
+  NWX_REQUIRE(c2w && rays_out && B > 0 && H > 0 && W > 0 && ray0 >= 0 && nrays >= 0);
+  NWX_REQUIRE(ray0 + nrays <= (int64_t)B * H * W);
+  if (nrays == 0) return NWX_OK;
+  const unsigned grid = (unsigned)((nrays + nwx::kRaygenThreads - 1) / nwx::kRaygenThreads);
+  auto st = (cudaStream_t)stream;
+  if (use_view_dirs)
+    nwx::raygen_kernel<true><<<grid, nwx::kRaygenThreads, 0, st>>>(c2w, H, W, fx, fy, cx, cy, near, far,
+                                                                  ray0, nrays, rays_out);
+  else
+    nwx::raygen_kernel<false><<<grid, nwx::kRaygenThreads, 0, st>>>(c2w, H, W, fx, fy, cx, cy, near, far,
+                                                                   ray0, nrays, rays_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+extern "C" int nwx_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals,
+                            const float* t_rand, float* z_out, void* stream) {
+  NWX_REQUIRE(rays && t_vals && z_out && ray_dim >= 8 && S >= 2 && N >= 0);
+  if (N == 0) return NWX_OK;
+  const int64_t total = N * S;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)nwx::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  nwx::coarse_z_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rays, ray_dim, total, S, t_vals,
+                                                                         t_rand, z_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+extern "C" int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream) {
+  NWX_REQUIRE(x && out && n >= 0);
+  if (n == 0) return NWX_OK;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)nwx::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  nwx::to8b_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}

@@ -1,0 +1,241 @@
+// K2: hierarchical importance resampling (sample_pdf, reference nerf/rays/rays.py:74-121) fused
+// with the coarse/fine depth merge sort(cat(z, z_samples)) (inference handler:243).
+//
+// One warp per ray.  Per ray the warp: stages z / weights in shared memory (coalesced loads),
+// builds the 63-entry CDF, inverts it for 128 uniforms with binary searches over shared memory,
+// and merges the sorted fine samples with the coarse depths by rank (merge-path), writing every
+// output row coalesced.  1.3 KB of HBM traffic per ray.
+//
+// Bit-exact indices.  The searchsorted result depends on every bit of the CDF, so the CDF is
+// built exactly as torch-CPU builds it (orders determined against the reference's output, see
+// DESIGN.md "bit-exact ops"; tests/golden/sample_pdf.npz pins it):
+//   * torch.sum over the 62 contiguous weights: ATen's AVX2 cascade (sum_stub is registered
+//     without an AVX-512 variant, so every x86 host runs the 8-lane kernel): with 8-float
+//     vectors v0..v6 and tail x56..x61:  p = v0+v4+v5+v6+v1+v2+v3 (lane-wise, in that order),
+//     total = ((0 + x56 + ... + x61) + p[0]) + ... + p[7].  cascade_sum_emul() implements the
+//     general-length rule (ilp 4, vec 8).
+//   * pdf = w / total: correctly rounded fp32 division.
+//   * torch.cumsum: fp32 input accumulated in DOUBLE, each output rounded to fp32.  pdf values
+//     are >= 1e-5/1.0007 > 2^-17 and sum to ~1, so every partial sum is an exact multiple of
+//     2^-40 below 2 and fits a double: any summation order gives the same doubles, and the warp
+//     scan is bit-identical to the sequential loop.
+//   * the lerp of rays.py:113-119 is evaluated op by op without FMA contraction.
+#include "nwx_common.cuh"
+
+namespace nwx {
+
+constexpr int kPdfWarps = 8;
+constexpr int kMaxBins = 128;     // M = Sc-1 <= 127
+constexpr int kMaxImp = 256;
+
+struct PdfSmem {
+  float bins[kMaxBins];
+  float cdf[kMaxBins];
+  float x[kMaxBins];          // weights + 1e-5, then pdf
+  float zc[kMaxBins];         // coarse depths
+  float smp[kMaxImp];         // fine samples (sorted in place when u is random)
+  float merged[kMaxBins + kMaxImp];
+};
+
+// torch.sum(x[0..n), dim=-1) on a contiguous fp32 row, n >= 8, bit-exact (see file header).
+__device__ __forceinline__ float cascade_sum_emul(const float* x, int n, int lane) {
+  const int V = n >> 3;            // full 8-float vectors
+  const int ilp = V >> 2;          // rows of 4 vectors handled by multi_row_sum (< 16 for n < 512)
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+  if (lane < 8) {
+    for (int i = 0; i < ilp; ++i) {
+      p0 = __fadd_rn(p0, x[(4 * i + 0) * 8 + lane]);
+      p1 = __fadd_rn(p1, x[(4 * i + 1) * 8 + lane]);
+      p2 = __fadd_rn(p2, x[(4 * i + 2) * 8 + lane]);
+      p3 = __fadd_rn(p3, x[(4 * i + 3) * 8 + lane]);
+    }
+    for (int i = 4 * ilp; i < V; ++i) p0 = __fadd_rn(p0, x[i * 8 + lane]);
+    p0 = __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3);
+  }
+  float acc = 0.f;
+  for (int k = V * 8; k < n; ++k) acc = __fadd_rn(acc, x[k]);       // scalar tail first
+#pragma unroll
+  for (int l = 0; l < 8; ++l) acc = __fadd_rn(acc, __shfl_sync(kFull, p0, l));
+  return acc;                                                        // identical in every lane
+}
+
+__device__ __forceinline__ int upper_bound(const float* a, int n, float v) {   // #(a[i] <= v)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int lower_bound(const float* a, int n, float v) {   // #(a[i] < v)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// In-warp bitonic sort of a[0..n2) in shared memory, n2 a power of two <= 256.
+__device__ __forceinline__ void warp_bitonic_sort(float* a, int n2, int lane) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n2 >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+        const int p = i | j;
+        const bool up = (i & k) == 0;
+        const float lo = a[i], hi = a[p];
+        if ((lo > hi) == up) { a[i] = hi; a[p] = lo; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// kFromCoarse: inputs are (z_c, w_c) [N,Sc] and bins/weights are derived as the handlers do
+// (inference handler:236-237); otherwise inputs are (bins [N,M], weights [N,M-1]) as in rays.py:74.
+template <bool kFromCoarse>
+__global__ void __launch_bounds__(kPdfWarps * 32)
+sample_pdf_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int Sc, int M,
+                  const float* __restrict__ u, const float* __restrict__ u_lin, int n_imp, int64_t N,
+                  float* __restrict__ z_samples, float* __restrict__ z_fine, int64_t* __restrict__ inds_out,
+                  float* __restrict__ z_std, float* __restrict__ cdf_out) {
+  __shared__ PdfSmem smem[kPdfWarps];
+  PdfSmem& sm = smem[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kPdfWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kPdfWarps;
+  const int nw = M - 1;                                         // number of pdf weights
+  const bool det = (u == nullptr);
+
+  for (int64_t ray = warp0; ray < N; ray += nwarps) {
+    // ---- stage inputs ----
+    if (kFromCoarse) {
+      for (int i = lane; i < Sc; i += 32) sm.zc[i] = ldg_stream(in_a + ray * Sc + i);
+      for (int i = lane; i < nw; i += 32)
+        sm.x[i] = __fadd_rn(ldg_stream(in_b + ray * Sc + i + 1), 1e-5f);            // rays.py:87, w[1:-1]
+      __syncwarp();
+      for (int i = lane; i < M; i += 32)
+        sm.bins[i] = __fmul_rn(0.5f, __fadd_rn(sm.zc[i + 1], sm.zc[i]));            // handler:236
+    } else {
+      for (int i = lane; i < M; i += 32) sm.bins[i] = ldg_stream(in_a + ray * M + i);
+      for (int i = lane; i < nw; i += 32) sm.x[i] = __fadd_rn(ldg_stream(in_b + ray * nw + i), 1e-5f);
+    }
+    __syncwarp();
+
+    // ---- CDF (rays.py:88-90) ----
+    const float total = cascade_sum_emul(sm.x, nw, lane);
+    double carry = 0.0;
+    if (lane == 0) sm.cdf[0] = 0.0f;
+    for (int base = 0; base < nw; base += 32) {
+      const int i = base + lane;
+      double v = (i < nw) ? (double)__fdiv_rn(sm.x[i], total) : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += up;
+      }
+      v += carry;
+      if (i < nw) sm.cdf[i + 1] = (float)v;
+      carry = __shfl_sync(kFull, v, 31);
+    }
+    __syncwarp();
+    if (cdf_out)
+      for (int i = lane; i < M; i += 32) cdf_out[ray * M + i] = sm.cdf[i];
+
+    // ---- invert (rays.py:103-119) ----
+    double s1 = 0.0;
+    bool sorted = true;
+    for (int base = 0; base < n_imp; base += 32) {
+      const int q = base + lane;
+      float smp = 0.f;
+      if (q < n_imp) {
+        const float uu = det ? __ldg(u_lin + q) : ldg_stream(u + ray * n_imp + q);
+        const int ind = upper_bound(sm.cdf, M, uu);                                   // :103 right=True
+        const int below = max(ind - 1, 0), above = min(ind, M - 1);                   // :104-105
+        const float cb = sm.cdf[below], ca = sm.cdf[above];
+        const float bb = sm.bins[below], ba = sm.bins[above];
+        float denom = __fsub_rn(ca, cb);                                              // :113
+        if (denom < 1e-5f) denom = 1.0f;                                              // :114
+        const float t = __fdiv_rn(__fsub_rn(uu, cb), denom);                          // :118
+        smp = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                         // :119
+        sm.smp[q] = smp;
+        z_samples[ray * n_imp + q] = smp;
+        if (inds_out) inds_out[ray * n_imp + q] = ind;
+        s1 += smp;
+      }
+      // sortedness probe (needed only to skip the sort): compare with the previous element
+      float prev = __shfl_up_sync(kFull, smp, 1);
+      if (lane == 0) prev = (base == 0) ? smp : sm.smp[base - 1];
+      if (q < n_imp && !(prev <= smp)) sorted = false;
+      __syncwarp();                              // sm.smp[base+31] is read by lane 0 next round
+    }
+    __syncwarp();
+
+    if (z_std) {                                                                      // handler:267
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(kFull, s1, o);
+      const double mean = s1 / n_imp;
+      double s2 = 0.0;
+      for (int q = lane; q < n_imp; q += 32) { const double dlt = sm.smp[q] - mean; s2 += dlt * dlt; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(kFull, s2, o);
+      if (lane == 0) z_std[ray] = (float)sqrt(s2 / n_imp);
+    }
+
+    // ---- merge = torch.sort(cat([z_c, z_samples])) values (handler:243) ----
+    if (kFromCoarse && z_fine) {
+      if (!__all_sync(kFull, sorted)) {          // random u (training): sort the samples first
+        int n2 = 1;
+        while (n2 < n_imp) n2 <<= 1;
+        for (int q = n_imp + lane; q < n2; q += 32) sm.smp[q] = INFINITY;
+        __syncwarp();
+        warp_bitonic_sort(sm.smp, n2, lane);
+      }
+      for (int i = lane; i < Sc; i += 32) {
+        const float v = sm.zc[i];
+        sm.merged[i + lower_bound(sm.smp, n_imp, v)] = v;       // coarse first on ties
+      }
+      for (int q = lane; q < n_imp; q += 32) {
+        const float v = sm.smp[q];
+        sm.merged[q + upper_bound(sm.zc, Sc, v)] = v;
+      }
+      __syncwarp();
+      const int tot = Sc + n_imp;
+      for (int i = lane; i < tot; i += 32) z_fine[ray * tot + i] = sm.merged[i];
+    }
+    __syncwarp();
+  }
+}
+
+static inline unsigned pdf_grid(int64_t N) {
+  int64_t blocks = (N + kPdfWarps - 1) / kPdfWarps;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace nwx
+
+extern "C" int nwx_sample_pdf(const float* z_c, const float* w_c, int Sc, const float* u, const float* u_lin,
+                              int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds,
+                              float* z_std, void* stream) {
+  NWX_REQUIRE(z_c && w_c && z_samples && (u || u_lin) && N >= 0);
+  NWX_REQUIRE(Sc >= 11 && Sc <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
+  if (N == 0) return NWX_OK;
+  nwx::sample_pdf_kernel<true><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
+      z_c, w_c, Sc, Sc - 1, u, u_lin, n_imp, N, z_samples, z_fine, inds, z_std, nullptr);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+extern "C" int nwx_sample_pdf_bins(const float* bins, const float* weights, int M, const float* u,
+                                   const float* u_lin, int n_imp, int64_t N, float* samples, int64_t* inds,
+                                   float* cdf_out, void* stream) {
+  NWX_REQUIRE(bins && weights && samples && (u || u_lin) && N >= 0);
+  NWX_REQUIRE(M >= 10 && M <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
+  if (N == 0) return NWX_OK;
+  nwx::sample_pdf_kernel<false><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
+      bins, weights, 0, M, u, u_lin, n_imp, N, samples, nullptr, inds, nullptr, cdf_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}

@@ -1,0 +1,150 @@
+"""Reference entry points of nerf/models/{embedding,nerf_model,model_utils}.py on the CUDA engine.
+
+Same class / function names, constructor arguments, state_dict keys and return values as the
+reference, so its callers (handlers, nerf/train.py) keep working; the arithmetic runs in the
+hand-written kernels of libnwx (fused PE + tcgen05 MLP, warp-scan compositing).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from ._lib import NwxError
+from .batch_utils import batchify
+from .rays import _engine_for
+
+img2mse = lambda x, y: torch.mean((x - y) ** 2)                                  # model_utils.py:7
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))   # :8
+to8b_np = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)                    # :9
+to8b = lambda x: _engine.to8b(x)                                                  # :10
+
+
+class Embedding:
+    """(x/s, sin(x/s * 2^k), cos(x/s * 2^k))_{k<num_freqs}  -- embedding.py:6-48."""
+
+    def __init__(self, num_freqs: int, scalar_factor: float = 1.0) -> None:
+        self._num_freqs = num_freqs
+        self._scalar_factor = scalar_factor
+        self._output_dim = 3 + 3 * 2 * num_freqs
+
+    @property
+    def output_dim(self) -> int:
+        return self._output_dim
+
+    @property
+    def num_freqs(self) -> int:
+        return self._num_freqs
+
+    @property
+    def scalar_factor(self) -> float:
+        return self._scalar_factor
+
+    def embed(self, inputs: torch.Tensor) -> torch.Tensor:
+        return _engine.embed(inputs, self._num_freqs, self._scalar_factor)
+
+
+class NeRFModel(nn.Module):
+    """8x256 ReLU MLP, skip after layer 4, view-direction branch -- nerf_model.py:10-83.
+
+    Parameters live in ordinary nn.Linear modules under the reference's attribute names, so
+    state_dict()/load_state_dict() and torch.manual_seed-initialisation are interchangeable with
+    the reference.  forward() runs the fused tcgen05 kernel on a bf16 image of the weights that is
+    re-packed whenever a parameter changed.  Only the architecture the reference instantiates
+    (D=8, W=256, 63/27-d inputs, skips=(4,), use_view_dirs=True) is implemented; anything else
+    raises (no fallback).
+    """
+
+    def __init__(self, D: int = 8, W: int = 256, input_ch: int = 3, input_ch_views: int = 3, output_ch: int = 4,
+                 skips: Tuple[int, ...] = (4,), use_view_dirs: bool = False):
+        super().__init__()
+        self._D, self._W, self._input_ch, self._input_ch_views = D, W, input_ch, input_ch_views
+        self._output_ch, self._skips, self._use_view_dirs = output_ch, tuple(skips), use_view_dirs
+        self._pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in self._skips else nn.Linear(W + input_ch, W)
+                                        for i in range(D - 1)])
+        self._views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        if use_view_dirs:
+            self._feature_linear = nn.Linear(W, W)
+            self._alpha_linear = nn.Linear(W, 1)
+            self._rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self._output_linear = nn.Linear(W, output_ch)
+        self._nwx_engine: Optional[_engine.Engine] = None
+        self._nwx_stamp = None
+
+    def _supported(self) -> bool:
+        return (self._D == 8 and self._W == 256 and self._input_ch == 63 and self._input_ch_views == 27
+                and self._skips == (4,) and self._use_view_dirs)
+
+    def _packed_engine(self) -> _engine.Engine:
+        if not self._supported():
+            raise NwxError("NeRFModel: only D=8, W=256, input_ch=63, input_ch_views=27, skips=(4,), "
+                           "use_view_dirs=True is implemented by the fused kernel")
+        params = list(self.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise NwxError("NeRFModel.forward: parameters must be on a CUDA device (call .cuda())")
+        stamp = (dev.index,) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._nwx_engine is None or self._nwx_engine.device != dev:
+            self._nwx_engine, self._nwx_stamp = _engine.Engine(dev), None
+        if stamp != self._nwx_stamp:
+            self._nwx_engine.load_weights(_engine.COARSE, self.state_dict())
+            self._nwx_stamp = stamp
+        return self._nwx_engine
+
+    def forward(self, x: torch.Tensor, show_endpoint: bool = False) -> torch.Tensor:
+        """x [P,90] = (embedded xyz 63, embedded view dir 27) -> [P,4] raw (rgb, sigma)."""
+        if show_endpoint:
+            raise NwxError("show_endpoint=True (endpoint_feat) is not implemented; every shipped config "
+                           "sets endpoint_feat: False")
+        lead = x.shape[:-1]
+        out = self._packed_engine().mlp_forward_embedded(_engine.COARSE, x.reshape(-1, x.shape[-1]))
+        return out.reshape(*lead, 4)
+
+    def forward_points(self, pts: torch.Tensor, viewdirs: torch.Tensor, pts_per_dir: int = 1) -> torch.Tensor:
+        """Fused path: raw points [P,3] and unit view directions (one per `pts_per_dir` points)."""
+        return self._packed_engine().mlp_forward_points(_engine.COARSE, pts, viewdirs, pts_per_dir)
+
+
+def _is_standard_embed(fn, num_freqs: int, scale: float) -> bool:
+    owner = getattr(fn, "__self__", None)
+    return isinstance(owner, Embedding) and owner.num_freqs == num_freqs and owner.scalar_factor == scale
+
+
+def run_network(inputs: torch.Tensor, viewdirs: Optional[torch.Tensor], fn: Callable, embed_fn: Callable,
+                embeddirs_fn: Optional[Callable], netchunk: Optional[int] = 1024 * 64) -> torch.Tensor:
+    """model_utils.py:13-30: [N,S,3] points (+ [N,3] view dirs) -> [N,S,4].
+
+    When `fn` is a NeRFModel and the embedders are the standard Embedding(10,10)/(4,1) pair the
+    whole call is ONE fused kernel (no embedding materialised, no chunk loop).  Any other callable
+    (e.g. the handlers' lambda around the fine model) takes the literal path: embed kernels,
+    concatenation, and `fn` per chunk."""
+    if (isinstance(fn, NeRFModel) and viewdirs is not None and _is_standard_embed(embed_fn, 10, 10)
+            and _is_standard_embed(embeddirs_fn, 4, 1) and inputs.dim() == 3):
+        n, s, _ = inputs.shape
+        return fn.forward_points(inputs.reshape(-1, 3), viewdirs, pts_per_dir=s).reshape(n, s, 4)
+    flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(flat)
+    if viewdirs is not None:
+        dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(dirs, [-1, dirs.shape[-1]]))], -1)
+    out = batchify(fn, netchunk)(embedded)
+    return torch.reshape(out, list(inputs.shape[:-1]) + [out.shape[-1]])
+
+
+def raw2outputs(raw: torch.Tensor, z_vals: torch.Tensor, rays_d: torch.Tensor, raw_noise_std: float = 0,
+                white_bkgd: bool = False, endpoint_feat: bool = False, cuda_enabled: bool = True):
+    """model_utils.py:33-100 -> (rgb_map, disp_map, acc_map, weights, depth_map, feat_map)."""
+    if endpoint_feat:
+        raise NwxError("endpoint_feat=True is not implemented (every shipped config sets it False)")
+    if not cuda_enabled or not raw.is_cuda:
+        raise NwxError("raw2outputs: the engine has no CPU path (cuda_enabled=False is the reference's CPU switch)")
+    noise = None
+    if raw_noise_std > 0.:
+        noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std      # model_utils.py:65
+    rgb, disp, acc, weights, depth = _engine.composite(raw, z_vals, rays_d, noise, white_bkgd)
+    return rgb, disp, acc, weights, depth, torch.tensor(0)

@@ -1,0 +1,119 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol include/nwx.h declares (no compute
+without a GPU), and the host-side logic around it (pose producer, config, state-dict plumbing,
+drop-in module structure, failure behaviour)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import nerf_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def nwx_mod():
+    import nwx
+    if not os.path.exists(nwx._lib.LIB_PATH):
+        nwx.build()
+    return nwx
+
+
+def test_library_exports_every_declared_symbol(nwx_mod):
+    header = open(os.path.join(ROOT, "include", "nwx.h")).read()
+    declared = sorted(set(re.findall(r"\b(nwx_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = nwx_mod.lib()
+    missing = [name for name in declared if not hasattr(lib, name)]
+    assert not missing, missing
+    from nwx._lib import PROTOTYPES
+    assert set(declared) == set(PROTOTYPES)                    # the binding covers the header one to one
+    assert lib.nwx_version() == 100
+    assert lib.nwx_error_string(0) == b"ok" and b"invalid" in lib.nwx_error_string(1)
+    assert b"fallback" in lib.nwx_error_string(3)
+
+
+def test_library_is_blackwell_native(nwx_mod):
+    """SASS evidence (B200_PROFILING.md): tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, bulk TMA ->
+    UBLKCP; and no legacy HMMA tensor path."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", nwx_mod._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    assert "UTCHMMA.2CTA" in sass                              # cta_group::2 variant present
+    assert not re.search(r"\bHMMA\b", sass)
+
+
+def test_no_gpu_means_error_not_fallback(nwx_mod):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nwx_mod.NwxError):
+        nwx_mod.Engine()
+    with pytest.raises(nwx_mod.NwxError):
+        nwx_mod.raw2outputs(torch.zeros(2, 64, 4), torch.zeros(2, 64), torch.zeros(2, 3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nerf-workspaces-explorer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "/root/reference" not in text, f
+
+
+def test_pose_producer_matches_reference(nwx_mod):
+    g = load_golden("poses36")
+    rng = np.random.RandomState(0)
+    x, z = rng.uniform(-2, 2), rng.uniform(-3, 1.5)
+    init = nwx_mod.COORD(x=x, y=-0.5, z=z, yaw=0.0, pitch=-90.0, roll=0.0)
+    views = [nwx_mod.COORD(yaw=-float(h), pitch=float(v)) for v in (-30, 0, 30) for h in range(0, 360, 30)]
+    poses = nwx_mod.get_camera_poses_from_list_of_coordinates(init, views)
+    assert poses.shape == (36, 4, 4) and poses.dtype == torch.float32
+    assert torch.allclose(poses, g["poses"], atol=1e-6, rtol=0)
+    assert nwx_mod.COORD() == (0.0,) * 6 and nwx_mod.HW(3, 4).w == 4
+
+
+def test_config_and_state_dict_plumbing(nwx_mod):
+    from nwx.config import default_config, number
+    from nwx.engine import STATE_KEYS, normalize_state_dict
+    cfg = default_config()
+    assert number(cfg["model"]["net_chunk"]) == 32768 and number(cfg["inference"]["chunk"]) == 8192
+    assert number(cfg["rendering"]["n_rays"]) == 1024 and number(7) == 7
+    sd = orc.init_state_dict(0)
+    assert tuple(STATE_KEYS) == tuple(orc.STATE_KEYS)
+    shipped = {k[1:]: v for k, v in sd.items()}                 # checkpoint style: no leading underscore
+    assert set(normalize_state_dict(shipped)) == set(sd)
+    H = nwx_mod.NeRFReplicaInferenceHandler
+    assert set(H.transform_state_dict(shipped)) == set(sd)
+    with pytest.raises(nwx_mod.NwxError):
+        normalize_state_dict({k: v for k, v in sd.items() if "alpha" not in k})
+    bad = dict(sd); bad["_pts_linears.0.weight"] = torch.zeros(128, 63)
+    with pytest.raises(nwx_mod.NwxError):
+        normalize_state_dict(bad)
+
+
+def test_drop_in_modules_on_cpu(nwx_mod):
+    torch.manual_seed(0)
+    m = nwx_mod.NeRFModel(8, 256, 63, 27, 5, use_view_dirs=True)
+    sd = orc.init_state_dict(0, alpha_bias=None)
+    assert list(m.state_dict()) == list(orc.STATE_KEYS)
+    assert all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)     # same construction order / RNG stream
+    assert sum(p.numel() for p in m.parameters()) == 595844
+    assert nwx_mod.Embedding(10, 10).output_dim == 63 and nwx_mod.Embedding(4, 1).output_dim == 27
+    h = nwx_mod.NeRFReplicaInferenceHandler("office_tokyo", "/nonexistent/model.ckpt")
+    assert (h._img_h, h._img_w, h._cx, h._cy) == (240, 320, 159.5, 119.5) and abs(h._fx - 160.0) < 1e-9
+    with pytest.raises(RuntimeError, match="cannot be found"):     # reference behaviour, handler:147-148
+        h.initialize_models()
+    with pytest.raises(RuntimeError):
+        h.engine
+    out = nwx_mod.batchify(lambda x: x * 2, 3)(torch.arange(10.))
+    assert torch.equal(out, torch.arange(10.) * 2)
+    parts = nwx_mod.batchify_rays(lambda r: {"a": r[:, 0]}, torch.arange(20.).reshape(10, 2), chunk=4)
+    assert torch.equal(parts["a"], torch.arange(0., 20., 2))

@@ -1,0 +1,137 @@
+"""GPU parity of the whole _volumetric_rendering path (inference and training variants) against
+the golden output of the reference handler, plus size-independent properties at 640x480.
+
+Tolerances (BASELINE.json north_star): ray / searchsorted indices exact given identical inputs
+(tests/test_gpu_kernels.py); rgb / acc within 1e-3 abs; depth within 1e-3 of the depth range
+(far - near = 9.9 m; SURVEY.md section 7 shows metres-scale depth cannot meet 1e-3 abs with bf16
+hidden activations); PSNR of the rendered rgb against the fp32 reference reported and > 60 dB."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+DEPTH_RANGE = 9.9
+
+
+def _nets():
+    gen = torch.Generator().manual_seed(0)
+    return orc.init_state_dict(0, generator=gen), orc.init_state_dict(0, generator=gen)
+
+
+@pytest.fixture(scope="module")
+def handler():
+    import nwx
+    h = nwx.NeRFReplicaInferenceHandler("office_tokyo", None)
+    h.load_state_dicts(*_nets())
+    return h
+
+
+def _check_maps(out, ref, tag):
+    for k in ("rgb_coarse", "rgb_fine", "acc_coarse", "acc_fine"):
+        err = float((out[k].cpu() - ref[k]).abs().max())
+        assert err <= 1e-3, (tag, k, err)
+    for k in ("depth_coarse", "depth_fine"):
+        err = float((out[k].cpu() - ref[k]).abs().max())
+        assert err <= 1e-3 * DEPTH_RANGE, (tag, k, err)
+    for k in ("disp_coarse", "disp_fine"):
+        rel = float(((out[k].cpu() - ref[k]).abs() / ref[k].abs().clamp(min=1e-3)).max())
+        assert rel <= 2e-3, (tag, k, rel)
+    mse = float(((out["rgb_fine"].cpu() - ref["rgb_fine"]) ** 2).mean())
+    assert -10 * math.log10(max(mse, 1e-20)) > 60.0, (tag, mse)
+
+
+def test_inference_chunk_vs_reference_handler_golden(handler):
+    g = load_golden("render_infer")
+    out = handler._volumetric_rendering(g["rays"].to(DEV))
+    assert tuple(out.keys()) == orc.REFERENCE_KEYS                 # the reference's 11-key dict
+    for k in orc.REFERENCE_KEYS:
+        assert out[k].shape == g[k].shape, k
+    _check_maps(out, g, "infer")
+    assert float((out["raw_coarse"].cpu() - g["raw_coarse"]).abs().max()) <= 1.5e-3
+    assert float((out["raw_fine"].cpu() - g["raw_fine"]).abs().max()) <= 1.5e-3
+    assert float((out["z_std"].cpu() - g["z_std"]).abs().max()) <= 2e-3
+    handler.check_numerics()
+    assert int(handler.last_flags.item()) == 0
+
+
+def test_stage_outputs_and_index_agreement(handler):
+    """Coarse depths are bit-exact; fine samples come from bf16-perturbed weights, so their
+    searchsorted indices are compared as an agreement rate (reported) and the sample values by
+    tolerance -- the exact-index claim is test_sample_pdf_* on identical inputs."""
+    g = load_golden("render_infer")
+    want = orc.REFERENCE_KEYS + ("z_vals_coarse", "weights_coarse", "z_samples", "inds", "z_vals_fine")
+    out = handler.engine.render_rays(g["rays"].to(DEV), 64, 128, False, want=want)
+    assert torch.equal(out["z_vals_coarse"].cpu(), g["z_vals_coarse"].contiguous())
+    assert float((out["weights_coarse"].cpu() - g["weights_coarse"]).abs().max()) <= 2e-4
+    agree = float((out["inds"].cpu() == g["inds"]).float().mean())
+    assert agree >= 0.97, agree
+    assert float((out["z_samples"].cpu() - g["z_samples"]).abs().max()) <= 2e-2
+    zf = out["z_vals_fine"]
+    assert bool((zf[:, 1:] >= zf[:, :-1]).all())
+
+
+def test_training_variant_vs_reference_golden(handler):
+    """Stratified jitter, sigma noise and random u injected exactly as the reference drew them."""
+    g = load_golden("render_train")
+    out = handler.engine.render_rays(g["rays"].to(DEV), 64, 128, False,
+                                     want=orc.REFERENCE_KEYS + ("z_vals_coarse", "z_vals_fine"),
+                                     t_rand=g["t_rand"].to(DEV), u=g["u"].to(DEV),
+                                     noise_coarse=g["noise_c"].to(DEV), noise_fine=g["noise_f"].to(DEV))
+    assert torch.equal(out["z_vals_coarse"].cpu(), g["z_vals_coarse"].contiguous())     # jittered depths: exact
+    _check_maps(out, g, "train")
+
+
+def test_render_coordinates_drop_in(handler):
+    import nwx
+    handler._img_h, handler._img_w = 24, 32                       # small frame; intrinsics as the handler derives them
+    handler._n_pix = 24 * 32
+    handler._fx = handler._fy = 16.0
+    handler._cx, handler._cy = 15.5, 11.5
+    init = nwx.COORD(x=0.3, y=-0.5, z=-1.0, yaw=0.0, pitch=-90.0, roll=0.0)
+    img = handler.render_coordinates(init, nwx.COORD(yaw=-30.0, pitch=30.0))
+    assert img.shape == (24, 32, 3) and img.dtype == np.uint8
+    pose = nwx.get_camera_poses_from_list_of_coordinates(init, [nwx.COORD(yaw=-30.0, pitch=30.0)])
+    ref = orc.render_image(pose, *_nets(), orc.RenderConfig(), 24, 32, 16.0, 16.0, 15.5, 11.5, 0.1, 10.0)
+    assert int(np.abs(img.astype(int) - ref.astype(int)).max()) <= 1            # uint8 image within one level
+    batch = handler.render_coordinates_batch(init, [nwx.COORD(yaw=-30.0, pitch=30.0), nwx.COORD(yaw=60.0)])
+    assert batch.shape == (2, 24, 32, 3) and np.array_equal(batch[0], img)
+
+
+def test_full_frame_properties_640x480():
+    """BASELINE config 2 shape (307 200 rays, 64+128).  The CPU oracle needs minutes per frame, so
+    this checks what must hold at any size: sharding invariance (bitwise), sortedness, ranges,
+    and oracle parity on a strided subset of the same rays."""
+    import nwx
+    from nwx import engine as E
+    eng = nwx.Engine(torch.device(DEV))
+    sd_c, sd_f = _nets()
+    eng.load_weights(E.COARSE, sd_c); eng.load_weights(E.FINE, sd_f)
+    H, W = 480, 640
+    fx, fy, cx, cy = orc.intrinsics(H, W)
+    pose = orc.synthetic_poses(36, 0)[7:8]
+    rays = eng.raygen(pose, H, W, fx, fy, cx, cy, 0.1, 10.0)
+    want = ("rgb_fine", "acc_fine", "depth_fine", "z_vals_fine", "weights_fine", "rgb8_fine")
+    full = eng.render_rays(rays, want=want)
+    assert int(full["flags"].item()) == 0
+    assert full["rgb_fine"].shape == (H * W, 3)
+    assert float(full["rgb_fine"].min()) >= 0.0 and float(full["rgb_fine"].max()) <= 1.0 + 1e-5
+    assert float(full["acc_fine"].max()) <= 1.0 + 1e-5
+    assert bool((full["z_vals_fine"][:, 1:] >= full["z_vals_fine"][:, :-1]).all())
+    assert torch.equal(full["rgb8_fine"].cpu(), torch.from_numpy(orc.to8b(full["rgb_fine"].cpu().numpy())))
+    # row-tile sharding (what the multi-GPU path does) reproduces the frame bit for bit
+    cuts = [0, 100 * W, 100 * W + 77, 300 * W, H * W]
+    parts = [eng.render_rays(rays[a:b], want=("rgb_fine",))["rgb_fine"] for a, b in zip(cuts[:-1], cuts[1:])]
+    assert torch.equal(torch.cat(parts, 0), full["rgb_fine"])
+    # oracle parity on every 601st ray of the frame
+    idx = torch.arange(0, H * W, 601)
+    with torch.no_grad():
+        ref = orc.volumetric_rendering(rays[idx.to(DEV)].cpu(), sd_c, sd_f, orc.RenderConfig(), train_mode=False)
+    assert float((full["rgb_fine"][idx.to(DEV)].cpu() - ref["rgb_fine"]).abs().max()) <= 1e-3
+    assert float((full["acc_fine"][idx.to(DEV)].cpu() - ref["acc_fine"]).abs().max()) <= 1e-3
+    assert float((full["depth_fine"][idx.to(DEV)].cpu() - ref["depth_fine"]).abs().max()) <= 1e-3 * DEPTH_RANGE
