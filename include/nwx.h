@@ -166,6 +166,14 @@ int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const nwx_render
 /* (255*clip(x,0,1)).astype(uint8) (model_utils.py:9) over n floats. */
 int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream);
 
+/* Per-stage device timing of nwx_render_rays (CUDA events on the caller's stream).  Stage order:
+ * coarse_z, dirbias(coarse), mlp(coarse), composite(coarse), sample_pdf, dirbias(fine), mlp(fine),
+ * composite(fine)+to8b.  nwx_ctx_stage_ms waits for the last recorded call and fills
+ * ms_out[NWX_NUM_STAGES] (host). */
+#define NWX_NUM_STAGES 8
+int nwx_ctx_set_profiling(nwx_ctx* ctx, int on);
+int nwx_ctx_stage_ms(nwx_ctx* ctx, float* ms_out);
+
 /* ---- introspection for bench/tests --------------------------------------------------------- */
 /* Number of kernels this library has launched since load (all contexts). */
 int64_t nwx_launch_count(void);

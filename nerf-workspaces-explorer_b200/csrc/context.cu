@@ -25,6 +25,10 @@ struct nwx_ctx {
   float* dbg_out = nullptr;      // optional tap target set by nwx_debug_tap
   int dbg_layer = -1;
   uint32_t* diag = nullptr;      // optional host-mapped diagnostics
+  // optional per-stage device timing of nwx_render_rays (bench.py: roofline of the dominant kernel)
+  bool profiling = false;
+  bool ev_recorded = false;
+  cudaEvent_t ev[NWX_NUM_STAGES + 1] = {};
 };
 
 namespace {
@@ -102,6 +106,8 @@ extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
     if (n.bview) cudaFree(n.bview);
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
+  for (auto e : ctx->ev)
+    if (e) cudaEventDestroy(e);
   delete ctx;
   return NWX_OK;
 }
@@ -131,6 +137,22 @@ extern "C" int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped) {
   return NWX_OK;
 }
 
+extern "C" int nwx_ctx_set_profiling(nwx_ctx* ctx, int on) {
+  NWX_REQUIRE(ctx);
+  if (on && !ctx->ev[0])
+    for (auto& e : ctx->ev) NWX_CUDA_TRY(cudaEventCreate(&e));
+  ctx->profiling = on != 0;
+  ctx->ev_recorded = false;
+  return NWX_OK;
+}
+
+extern "C" int nwx_ctx_stage_ms(nwx_ctx* ctx, float* ms_out) {
+  NWX_REQUIRE(ctx && ms_out && ctx->ev_recorded);
+  NWX_CUDA_TRY(cudaEventSynchronize(ctx->ev[NWX_NUM_STAGES]));
+  for (int i = 0; i < NWX_NUM_STAGES; ++i) NWX_CUDA_TRY(cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
+  return NWX_OK;
+}
+
 extern "C" int nwx_ctx_reserve(nwx_ctx* ctx, int64_t max_rays, int n_samples, int n_importance) {
   NWX_REQUIRE(ctx && max_rays > 0 && n_samples > 0 && n_importance >= 0);
   return ensure_scratch(ctx, plan_scratch(max_rays, n_samples, n_importance).total);
@@ -138,11 +160,12 @@ extern "C" int nwx_ctx_reserve(nwx_ctx* ctx, int64_t max_rays, int n_samples, in
 
 static int run_mlp(nwx_ctx* ctx, int which, const float* rays, int ray_dim, const float* z, const float* pts,
                    const float* dirs, int dir_stride, int64_t n_dir, int64_t P, int S, float* dirbias,
-                   float* raw_out, cudaStream_t st, const float* embedded = nullptr) {
+                   float* raw_out, cudaStream_t st, const float* embedded = nullptr, cudaEvent_t mid = nullptr) {
   const nwx::PackedNet& net = ctx->net[which];
   if (!net.loaded) return NWX_E_NO_WEIGHTS;
   int rc = nwx::launch_dirbias(net, dirs, dir_stride, n_dir, embedded != nullptr, dirbias, st);
   if (rc) return rc;
+  if (mid) NWX_CUDA_TRY(cudaEventRecord(mid, st));
   nwx::MlpArgs a{};
   a.rays = rays; a.z = z; a.pts = pts; a.embedded = embedded; a.wimg = net.wimg; a.dirbias = dirbias; a.raw_out = raw_out;
   a.dbg_out = ctx->dbg_out; a.dbg_layer = ctx->dbg_layer; a.diag = ctx->diag;
@@ -204,15 +227,30 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   float* rgb_c = out->rgb_coarse ? out->rgb_coarse : s + pl.rgb_c;
   float* dirb = s + pl.dirbias;
   if (out->flags) NWX_CUDA_TRY(cudaMemsetAsync(out->flags, 0, sizeof(int32_t), st));
+  const bool prof = ctx->profiling;
+  auto mark = [&](int i) -> int {
+    if (prof) NWX_CUDA_TRY(cudaEventRecord(ctx->ev[i], st));
+    return NWX_OK;
+  };
 
+  if ((rc = mark(0))) return rc;
   if ((rc = nwx_coarse_z(rays, rd, N, Sc, o->t_vals, o->t_rand, z_c, st))) return rc;
-  if ((rc = run_mlp(ctx, NWX_NET_COARSE, rays, rd, z_c, nullptr, rays + 8, rd, N, N * Sc, Sc, dirb, raw_c, st))) return rc;
+  if ((rc = mark(1))) return rc;
+  if ((rc = run_mlp(ctx, NWX_NET_COARSE, rays, rd, z_c, nullptr, rays + 8, rd, N, N * Sc, Sc, dirb, raw_c, st, nullptr,
+                    prof ? ctx->ev[2] : nullptr))) return rc;
+  if ((rc = mark(3))) return rc;
   if ((rc = nwx_composite_fwd(raw_c, z_c, rays + 3, rd, o->noise_coarse, N, Sc, o->white_bkgd, rgb_c, out->disp_coarse,
                               out->acc_coarse, out->depth_coarse, w_c, out->flags, st))) return rc;
+  if ((rc = mark(4))) return rc;
   if ((rc = nwx_sample_pdf(z_c, w_c, Sc, o->u, o->u_lin, Ni, N, z_s, z_f, out->inds, out->z_std, st))) return rc;
-  if ((rc = run_mlp(ctx, NWX_NET_FINE, rays, rd, z_f, nullptr, rays + 8, rd, N, N * Sf, Sf, dirb, raw_f, st))) return rc;
+  if ((rc = mark(5))) return rc;
+  if ((rc = run_mlp(ctx, NWX_NET_FINE, rays, rd, z_f, nullptr, rays + 8, rd, N, N * Sf, Sf, dirb, raw_f, st, nullptr,
+                    prof ? ctx->ev[6] : nullptr))) return rc;
+  if ((rc = mark(7))) return rc;
   if ((rc = nwx_composite_fwd(raw_f, z_f, rays + 3, rd, o->noise_fine, N, Sf, o->white_bkgd, out->rgb_fine, out->disp_fine,
                               out->acc_fine, out->depth_fine, out->weights_fine, out->flags, st))) return rc;
   if (out->rgb8_fine && (rc = nwx_to8b(out->rgb_fine, N * 3, out->rgb8_fine, st))) return rc;
+  if ((rc = mark(8))) return rc;
+  ctx->ev_recorded = prof;
   return NWX_OK;
 }

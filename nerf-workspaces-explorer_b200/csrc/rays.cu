@@ -125,9 +125,9 @@ extern "C" int nwx_embed(const float* x, int64_t P, int num_freqs, float scalar_
 extern "C" int nwx_raygen(const float* c2w, int B, int H, int W, float fx, float fy, float cx, float cy,
                           float near, float far, int use_view_dirs, int64_t ray0, int64_t nrays,
                           float* rays_out, void* stream) {
-  NWX_REQUIRE(c2w && rays_out && B > 0 && H > 0 && W > 0 && ray0 >= 0 && nrays >= 0);
-  NWX_REQUIRE(ray0 + nrays <= (int64_t)B * H * W);
-  if (nrays == 0) return NWX_OK;
+  NWX_REQUIRE(B > 0 && H > 0 && W > 0 && ray0 >= 0 && nrays >= 0 && ray0 + nrays <= (int64_t)B * H * W);
+  if (nrays == 0) return NWX_OK;                 // an empty shard is legal (and has a null output pointer)
+  NWX_REQUIRE(c2w && rays_out);
   const unsigned grid = (unsigned)((nrays + nwx::kRaygenThreads - 1) / nwx::kRaygenThreads);
   auto st = (cudaStream_t)stream;
   if (use_view_dirs)

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "nwx_sample_pdf": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nwx_sample_pdf_bins": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "nwx_ctx_reserve": (_i, [_vp, _i64, _i, _i]),
+    "nwx_ctx_set_profiling": (_i, [_vp, _i]),
+    "nwx_ctx_stage_ms": (_i, [_vp, C.POINTER(_f)]),
     "nwx_render_rays": (_i, [_vp, _vp, _i64, C.POINTER(RenderOpts), C.POINTER(RenderOut), _vp]),
     "nwx_to8b": (_i, [_vp, _i64, _vp, _vp]),
     "nwx_launch_count": (_i64, []),

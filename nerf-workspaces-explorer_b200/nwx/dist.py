@@ -1,0 +1,66 @@
+"""Multi-GPU rendering: rays shard naturally, so a frame (or a multi-view batch) is cut into
+contiguous ray ranges, one per rank (= row tiles of the image when the range is a multiple of W);
+weights are replicated; the only exchange is one all-gather of the uint8 pixel tiles (NCCL over
+NVLink on GPUs, gloo in the CPU tests).  The reference has no distributed code."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced split of `total` rays: the first total % world ranks get one more."""
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def gather_tiles(local: torch.Tensor, total: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather per-rank tiles [count_r, C] (ranges from shard_range) into [total, C] on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    counts = [shard_range(total, r, world)[1] for r in range(world)]
+    if len(set(counts)) == 1:
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    width = max(counts)                      # ragged split: pad to the widest tile, then trim
+    padded = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+
+
+def render_sharded(total_rays: int, render_range: Callable[[int, int], torch.Tensor],
+                   group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """render_range(start, count) -> [count, C] for this rank's range; returns the full [total, C]."""
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    start, count = shard_range(total_rays, rank, world)
+    return gather_tiles(render_range(start, count), total_rays, group)
+
+
+def render_poses_sharded(handler, c2w: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """[B,4,4] poses -> uint8 [B,H,W,3] on every rank, each rank rendering 1/world of the B*H*W rays."""
+    eng = handler.engine
+    H, W = handler._img_h, handler._img_w
+    c2w_dev = c2w.to(eng.device, dtype=torch.float32)
+
+    def render_range(start: int, count: int) -> torch.Tensor:
+        rgb8 = torch.empty((count, 3), device=eng.device, dtype=torch.uint8)
+        step = handler.max_rays_per_launch
+        for s in range(0, count, step):
+            n = min(step, count - s)
+            rays = eng.raygen(c2w_dev, H, W, handler._fx, handler._fy, handler._cx, handler._cy,
+                              handler._depth_close_bound, handler._depth_far_bound, True, ray0=start + s, nrays=n)
+            eng.render_rays(rays, handler._n_samples, handler._n_importance, handler._white_bkgd,
+                            want=("rgb8_fine",), out={"rgb8_fine": rgb8[s:s + n]})
+        return rgb8
+
+    return render_sharded(c2w.shape[0] * H * W, render_range, group).view(c2w.shape[0], H, W, 3)

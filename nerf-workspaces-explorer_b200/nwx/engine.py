@@ -132,6 +132,18 @@ class Engine:
     def debug_diag(self, pinned: Optional[torch.Tensor]) -> None:
         check(self._lib.nwx_debug_diag(self._ctx, _ptr(pinned)), "nwx_debug_diag")
 
+    STAGES = ("coarse_z", "dirbias_coarse", "mlp_coarse", "composite_coarse", "sample_pdf", "dirbias_fine",
+              "mlp_fine", "composite_fine")
+
+    def set_profiling(self, on: bool) -> None:
+        check(self._lib.nwx_ctx_set_profiling(self._ctx, int(on)), "nwx_ctx_set_profiling")
+
+    def stage_ms(self) -> Dict[str, float]:
+        """Device time of each stage of the last render_rays call (waits for it)."""
+        buf = (C.c_float * len(self.STAGES))()
+        check(self._lib.nwx_ctx_stage_ms(self._ctx, buf), "nwx_ctx_stage_ms")
+        return dict(zip(self.STAGES, [float(v) for v in buf]))
+
     def reserve(self, max_rays: int, n_samples: int = 64, n_importance: int = 128) -> None:
         check(self._lib.nwx_ctx_reserve(self._ctx, max_rays, n_samples, n_importance), "nwx_ctx_reserve")
 
