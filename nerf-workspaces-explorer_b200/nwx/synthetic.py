@@ -32,7 +32,7 @@ def random_state_dicts(seed: int = 0, alpha_bias: float = 0.1) -> Tuple[Dict[str
     """Coarse and fine weights exactly as the reference handler would create them under
     torch.manual_seed(seed) (inference handler:106-119), with _alpha_linear.bias pinned so the
     density sign at the far sample is not a coin flip."""
-    with torch.random.fork_rng():
+    with torch.random.fork_rng(devices=[]):       # CPU generator only
         torch.manual_seed(seed)
         nets = [NeRFModel(8, 256, 63, 27, 5, use_view_dirs=True) for _ in range(2)]
     out = []
