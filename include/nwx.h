@@ -166,6 +166,37 @@ int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const nwx_render
 /* (255*clip(x,0,1)).astype(uint8) (model_utils.py:9) over n floats. */
 int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream);
 
+/* ---- training: the autograd part of NeRFReplicaTrainingHandler.step (training handler:277-315) -- */
+/* Master parameters, gradients and Adam moments of one network are flat fp32 device buffers of
+ * NWX_PARAMS_PER_NET floats in state_dict order; nwx_param_offsets gives the 24 tensor offsets. */
+int nwx_param_offsets(int* offsets24 /* host, 24 ints */);
+
+/* Re-pack one network (bf16 forward images, transposed images for the backward, device-side
+ * biases/heads) from its flat master parameters.  Stream-ordered, no host synchronisation; call
+ * after every optimiser step.  (nwx_load_weights is the inference-time equivalent.) */
+int nwx_train_pack(nwx_ctx* ctx, int which, const float* params_flat, void* stream);
+
+typedef struct nwx_train_io {
+  const float* rays;       /* [N, ray_dim] sampled rays (training handler:341-370)              */
+  const float* gt_rgb;     /* [N,3] ground-truth pixels                                         */
+  float* grad_coarse;      /* out: [NWX_PARAMS_PER_NET] d(loss)/d(params), overwritten          */
+  float* grad_fine;        /* out                                                               */
+  double* loss;            /* out: [2] = mse(rgb_coarse, gt), mse(rgb_fine, gt) (handler:291-298) */
+  float* rgb_coarse;       /* optional out [N,3]                                                */
+  float* rgb_fine;         /* optional out [N,3]                                                */
+} nwx_train_io;
+
+/* Forward in training mode (jitter t_rand, noise, random u from opts; training handler:534-618),
+ * loss = mse(rgb_coarse) + mse(rgb_fine), backward to both networks' parameters.  What
+ * total_loss.backward() (handler:305-308) computes; no gradient flows through z_samples (:580). */
+int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N, const nwx_render_opts* opts,
+                      void* stream);
+
+/* torch.optim.Adam step (default betas/eps are the caller's to pass; handler:234) on flat buffers;
+ * grads are multiplied by grad_scale first (1/world_size after a sum all-reduce). step is 1-based. */
+int nwx_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* Per-stage device timing of nwx_render_rays (CUDA events on the caller's stream).  Stage order:
  * coarse_z, dirbias(coarse), mlp(coarse), composite(coarse), sample_pdf, dirbias(fine), mlp(fine),
  * composite(fine)+to8b.  nwx_ctx_stage_ms waits for the last recorded call and fills

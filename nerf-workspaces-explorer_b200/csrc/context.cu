@@ -26,6 +26,11 @@ struct nwx_ctx {
   int dbg_layer = -1;
   uint32_t* diag = nullptr;      // optional host-mapped diagnostics
   // optional per-stage device timing of nwx_render_rays (bench.py: roofline of the dominant kernel)
+  // training scratch (activation / gradient tile images, dW partials, ...), grown on demand
+  uint8_t* tscratch = nullptr;
+  size_t tscratch_bytes = 0;
+  float* partial = nullptr;      // [n_partials][NWX_PARAMS_PER_NET], zero-initialised once
+  int n_partials = 0;
   bool profiling = false;
   bool ev_recorded = false;
   cudaEvent_t ev[NWX_NUM_STAGES + 1] = {};
@@ -106,6 +111,12 @@ extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
     if (n.bview) cudaFree(n.bview);
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->tscratch) cudaFree(ctx->tscratch);
+  if (ctx->partial) cudaFree(ctx->partial);
+  for (auto& n : ctx->net) {
+    if (n.wimg_t) cudaFree(n.wimg_t);
+    if (n.gconsts) cudaFree(n.gconsts);
+  }
   for (auto e : ctx->ev)
     if (e) cudaEventDestroy(e);
   delete ctx;
@@ -252,5 +263,134 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   if (out->rgb8_fine && (rc = nwx_to8b(out->rgb_fine, N * 3, out->rgb8_fine, st))) return rc;
   if ((rc = mark(8))) return rc;
   ctx->ev_recorded = prof;
+  return NWX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training: forward + backward of one ray batch (the autograd part of
+// NeRFReplicaTrainingHandler.step, training handler:277-308), optimiser step, re-pack
+// ------------------------------------------------------------------------------------------------
+extern "C" int nwx_param_offsets(int* offsets24) {
+  NWX_REQUIRE(offsets24);
+  for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) offsets24[i] = nwx::flat_offsets()[i];
+  return NWX_OK;
+}
+
+extern "C" int nwx_train_pack(nwx_ctx* ctx, int which, const float* params_flat, void* stream) {
+  NWX_REQUIRE(ctx && params_flat && (which == 0 || which == 1));
+  return nwx::train_pack(ctx->net[which], params_flat, (cudaStream_t)stream);
+}
+
+extern "C" int nwx_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int step, float grad_scale, void* stream) {
+  NWX_REQUIRE(params && grads && m && v && n >= 0 && step >= 1);
+  if (n == 0) return NWX_OK;
+  return nwx::launch_adam(params, grads, m, v, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+
+namespace {
+struct TrainPlan {
+  size_t acts_c, acts_f, gimg, hv_c, hv_f, d_raw_c, d_raw_f, pe_dir, d_rgb_c, d_rgb_f, rgb_c, rgb_f, total;
+};
+TrainPlan plan_train(int64_t N, int Sc, int Ni) {
+  TrainPlan p{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
+  const int Sf = Sc + Ni;
+  const int64_t tc = (N * Sc + 127) / 128, tf = (N * Sf + 127) / 128;
+  p.acts_c = take(nwx::act_image_bytes(tc));
+  p.acts_f = take(nwx::act_image_bytes(tf));
+  p.gimg = take(nwx::grad_image_bytes(tf));            // reused: coarse backward, then fine backward
+  p.hv_c = take((size_t)N * Sc * nwx::kViewHidden * 4);
+  p.hv_f = take((size_t)N * Sf * nwx::kViewHidden * 4);
+  p.d_raw_c = take((size_t)N * Sc * 16);
+  p.d_raw_f = take((size_t)N * Sf * 16);
+  p.pe_dir = take((size_t)N * nwx::kPeDir * 4);
+  p.d_rgb_c = take((size_t)N * 12);
+  p.d_rgb_f = take((size_t)N * 12);
+  p.rgb_c = take((size_t)N * 12);
+  p.rgb_f = take((size_t)N * 12);
+  p.total = off;
+  return p;
+}
+}  // namespace
+
+extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N, const nwx_render_opts* o, void* stream) {
+  NWX_REQUIRE(ctx && io && o && io->rays && io->gt_rgb && io->grad_coarse && io->grad_fine && io->loss && N > 0);
+  NWX_REQUIRE(o->n_samples >= 11 && o->n_samples <= 128 && o->n_importance >= 1 && o->n_importance <= 128);
+  NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin));
+  for (int w = 0; w < 2; ++w)
+    if (!ctx->net[w].loaded || !ctx->net[w].gconsts || !ctx->net[w].wimg_t) return NWX_E_NO_WEIGHTS;   // nwx_train_pack first
+  auto st = (cudaStream_t)stream;
+  const int Sc = o->n_samples, Ni = o->n_importance, Sf = Sc + Ni, rd = o->ray_dim;
+  const ScratchPlan pl = plan_scratch(N, Sc, Ni);
+  int rc = ensure_scratch(ctx, pl.total);
+  if (rc) return rc;
+  const TrainPlan tp = plan_train(N, Sc, Ni);
+  if (tp.total > ctx->tscratch_bytes) {
+    if (ctx->tscratch) NWX_CUDA_TRY(cudaFree(ctx->tscratch));
+    ctx->tscratch = nullptr; ctx->tscratch_bytes = 0;
+    NWX_CUDA_TRY(cudaMalloc(&ctx->tscratch, tp.total));
+    ctx->tscratch_bytes = tp.total;
+  }
+  if (!ctx->partial) {
+    ctx->n_partials = nwx::num_sms();
+    const size_t bytes = (size_t)ctx->n_partials * NWX_PARAMS_PER_NET * sizeof(float);
+    NWX_CUDA_TRY(cudaMalloc(&ctx->partial, bytes));
+    NWX_CUDA_TRY(cudaMemsetAsync(ctx->partial, 0, bytes, st));
+  }
+  float* s = ctx->scratch;
+  uint8_t* ts = ctx->tscratch;
+  float *z_c = s + pl.z_c, *raw_c = s + pl.raw_c, *w_c = s + pl.w_c, *z_s = s + pl.z_s, *z_f = s + pl.z_f,
+        *raw_f = s + pl.raw_f, *dirb = s + pl.dirbias;
+  float* rgb_c = io->rgb_coarse ? io->rgb_coarse : reinterpret_cast<float*>(ts + tp.rgb_c);
+  float* rgb_f = io->rgb_fine ? io->rgb_fine : reinterpret_cast<float*>(ts + tp.rgb_f);
+  float* hv[2] = {reinterpret_cast<float*>(ts + tp.hv_c), reinterpret_cast<float*>(ts + tp.hv_f)};
+  float* d_raw[2] = {reinterpret_cast<float*>(ts + tp.d_raw_c), reinterpret_cast<float*>(ts + tp.d_raw_f)};
+  float* d_rgb[2] = {reinterpret_cast<float*>(ts + tp.d_rgb_c), reinterpret_cast<float*>(ts + tp.d_rgb_f)};
+  uint8_t* acts[2] = {ts + tp.acts_c, ts + tp.acts_f};
+  float* pe_dir = reinterpret_cast<float*>(ts + tp.pe_dir);
+
+  // ---- forward (training handler:534-618), operands saved for the backward ----
+  for (int w = 0; w < 2; ++w) {        // this step's biases / heads -> constant bank (stream-ordered D2D)
+    if ((rc = nwx::upload_fwd_train_consts(w, ctx->net[w].gconsts, st))) return rc;
+    if ((rc = nwx::upload_train_consts(w, ctx->net[w].gconsts, st))) return rc;
+  }
+  auto fwd = [&](int which, const float* z, int S, float* raw) -> int {
+    const nwx::PackedNet& net = ctx->net[which];
+    int r = nwx::launch_dirbias(net, io->rays + 8, rd, N, false, dirb, st);
+    if (r) return r;
+    nwx::MlpArgs a{};
+    a.which = which;
+    a.rays = io->rays; a.z = z; a.wimg = net.wimg; a.dirbias = dirb; a.raw_out = raw; a.diag = ctx->diag;
+    a.acts = acts[which]; a.hv_out = hv[which]; a.P = N * S; a.ray_dim = rd; a.S = S;
+    return nwx::launch_mlp_train_forward(net, a, st);
+  };
+  if ((rc = nwx_coarse_z(io->rays, rd, N, Sc, o->t_vals, o->t_rand, z_c, st))) return rc;
+  if ((rc = fwd(NWX_NET_COARSE, z_c, Sc, raw_c))) return rc;
+  if ((rc = nwx_composite_fwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, N, Sc, o->white_bkgd, rgb_c, nullptr, nullptr,
+                              nullptr, w_c, nullptr, st))) return rc;
+  if ((rc = nwx_sample_pdf(z_c, w_c, Sc, o->u, o->u_lin, Ni, N, z_s, z_f, nullptr, nullptr, st))) return rc;
+  if ((rc = fwd(NWX_NET_FINE, z_f, Sf, raw_f))) return rc;
+  if ((rc = nwx_composite_fwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, N, Sf, o->white_bkgd, rgb_f, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, st))) return rc;
+  // ---- loss (training handler:291-305) and backward through compositing; z_samples is detached (:580) ----
+  if ((rc = nwx::launch_mse_grad(rgb_c, rgb_f, io->gt_rgb, N, d_rgb[0], d_rgb[1], io->loss, st))) return rc;
+  if ((rc = nwx_composite_bwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, nullptr, d_rgb[0], N, Sc, o->white_bkgd,
+                              d_raw[0], st))) return rc;
+  if ((rc = nwx_composite_bwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, nullptr, d_rgb[1], N, Sf, o->white_bkgd,
+                              d_raw[1], st))) return rc;
+  if ((rc = nwx::launch_embed(io->rays + 8, rd, N, 4, 1.0f, pe_dir, st))) return rc;   // pe(viewdir) per ray
+  // ---- backward through the two MLPs ----
+  float* grads[2] = {io->grad_coarse, io->grad_fine};
+  const int S[2] = {Sc, Sf};
+  for (int w = 0; w < 2; ++w) {
+    NWX_CUDA_TRY(cudaMemsetAsync(grads[w], 0, sizeof(float) * NWX_PARAMS_PER_NET, st));
+    nwx::TrainBwdArgs b{};
+    b.d_raw = d_raw[w]; b.hv = hv[w]; b.acts = acts[w]; b.gimg = ts + tp.gimg; b.partial = ctx->partial;
+    b.pe_dir = pe_dir; b.grad = grads[w]; b.diag = ctx->diag; b.P = N * S[w]; b.S = S[w]; b.max_partials = ctx->n_partials;
+    b.which = w;
+    if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st))) return rc;
+  }
   return NWX_OK;
 }

@@ -27,18 +27,9 @@
 // Numerics: bf16 operands (PE features, weights, hidden activations), fp32 accumulation and
 // biases; the sigma head, the 27-d view-direction term of the views layer and the rgb head are
 // evaluated in fp32 on CUDA cores (oracle model: mlp_forward_bf16_emul).
-#include "mlp.cuh"
-#include "sm100_ptx.cuh"
+#include "mlp_device.cuh"
 
 namespace nwx {
-
-using namespace ptx;
-
-constexpr int kTileM = 128;                     // points per tile (= TMEM lanes)
-constexpr int kThreads = 512;
-constexpr int kHBytes = kTileM * kHidden * 2;   // 65536: one activation tile, 4 K-blocks of 16 KB
-constexpr int kABlock = kTileM * 64 * 2;        // 16384: one [128 x 64] bf16 K-block of A
-constexpr uint32_t kSpinLimit = 1u << 24;
 
 // chunk schedule: layer 5 is split so that a chunk never needs more than 4 resident K-blocks
 constexpr int kNumChunks = 11;
@@ -47,47 +38,6 @@ __device__ __forceinline__ int chunk_kb0(int c) { return c == 6 ? 1 : 0; }
 __device__ __forceinline__ int chunk_nkb(int c) { return (c == 0 || c == 5) ? 1 : 4; }
 __device__ __forceinline__ int layer_gkb0(int l) {     // global K-block index of a layer's first K-block
   return l == 0 ? 0 : (l <= 5 ? 1 + 4 * (l - 1) : 22 + 4 * (l - 6));
-}
-
-template <bool kPair, int kStages>
-struct SmemLayout {
-  static constexpr uint32_t kStageBytes = kPair ? kKBlockBytes / 2 : kKBlockBytes;
-  static constexpr uint32_t h0 = 0;
-  static constexpr uint32_t pe0 = 2 * kHBytes;
-  static constexpr uint32_t w0 = pe0 + 2 * kABlock;
-  static constexpr uint32_t bar0 = w0 + kStages * kStageBytes;
-  // barrier slots (8 B each)
-  static constexpr uint32_t w_full = bar0;
-  static constexpr uint32_t w_empty = w_full + 8 * kStages;
-  static constexpr uint32_t w_peer = w_empty + 8 * kStages;
-  static constexpr uint32_t acc_full = w_peer + 8 * kStages;
-  static constexpr uint32_t a_ready = acc_full + 16;
-  static constexpr uint32_t pe_ready = a_ready + 16;
-  static constexpr uint32_t pe_free = pe_ready + 16;
-  static constexpr uint32_t tmem_slot = pe_free + 16;
-  static constexpr uint32_t total = tmem_slot + 16;
-  static constexpr uint32_t alloc_bytes = total + 1024;   // slack for manual 1024 B alignment
-};
-
-struct WaitCtx {
-  uint32_t* diag;
-  uint32_t code;
-};
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) {                  // never hang the GPU: report and abort the grid
-      if (w.diag) {
-        w.diag[0] = 0xDEAD0000u | w.code;
-        w.diag[1] = blockIdx.x;
-        w.diag[2] = bar;
-        w.diag[3] = parity;
-        __threadfence_system();
-      }
-      __trap();
-    }
-  }
 }
 
 // 63 positional-encoding features of one point (+1 zero pad) as 32 packed bf16 pairs.
@@ -112,14 +62,26 @@ __device__ __forceinline__ void encode_point(float px, float py, float pz, uint3
   for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
 }
 
+// Training: biases/heads change every step, so they are refreshed by a stream-ordered
+// device-to-device copy into the constant bank (no host round trip) instead of riding in the
+// launch parameters.  (train.cu keeps its own copy for the backward kernels: __constant__
+// symbols are per translation unit without relocatable device code.)
+__constant__ MlpConsts c_fwd_train_consts[2];
+
+int upload_fwd_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st) {
+  NWX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_fwd_train_consts, dev_src, sizeof(MlpConsts), (size_t)which * sizeof(MlpConsts),
+                                       cudaMemcpyDeviceToDevice, st));
+  return NWX_OK;
+}
+
 enum { kEpiRelu = 0, kEpiReluSigma = 1, kEpiLinear = 2 };
 
 // Hidden-layer epilogue of one thread (= one point / TMEM lane) over its 128-column half:
 // accumulator -> +bias -> (ReLU) -> bf16 -> the next layer's swizzled A-operand tile.
 // Returns this half's partial of the fp32 sigma head when kMode == kEpiReluSigma.
-template <int kMode, bool kTap>
+template <int kMode, bool kTap, bool kSave>
 __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, uint32_t d_tmem, uint32_t hrow,
-                                                 int row, int wg, float* tap_row) {
+                                                 int row, int wg, float* tap_row, uint8_t* grow) {
   float sig = 0.f;
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
@@ -147,14 +109,22 @@ __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, ui
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    if (kSave) {                                   // training: keep the same tile image in HBM for the backward
+      uint8_t* gk = grow + (size_t)(col >> 6) * kTileImgBytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(gk + (((j0 + q) ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
   }
   return sig;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst) {
+mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst_param) {
   using L = SmemLayout<kPair, kStages>;
+  const MlpConsts& cst = kTrain ? c_fwd_train_consts[args.which] : cst_param;
   constexpr int kCG = kPair ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -312,6 +282,13 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (kPair) mbar_arrive_cluster(leader(sbase + L::pe_ready + 8 * t));
           else mbar_arrive(sbase + L::pe_ready + 8 * t);
         }
+        if (kTrain && args.acts != nullptr && tile_of(it, t) < args.n_tiles) {
+          uint8_t* g = args.acts + tile_img_offset(act_slot_kb0(0), 1, args.n_tiles, tile_of(it, t), 0) + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(g + ((j ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
       }
     }
   } else if (warp >= 8) {
@@ -333,13 +310,19 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (kTap && args.dbg_out != nullptr && args.dbg_layer == l && p < P) tap_row = args.dbg_out + p * kHidden;
           if (l < 9) {
             const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
+            const bool save = kTrain && args.acts != nullptr && tile_of(it, t) < args.n_tiles;
+            uint8_t* grow = save ? args.acts + tile_img_offset(act_slot_kb0(l + 1), 4, args.n_tiles, tile_of(it, t), 0) + row * 128
+                                 : nullptr;
             if (l == 7) {
-              const float sig = epilogue_hidden<kEpiReluSigma, kTap>(cst, l, d_tmem, hrow, row, wg, tap_row);
+              const float sig = save ? epilogue_hidden<kEpiReluSigma, kTap, true>(cst, l, d_tmem, hrow, row, wg, tap_row, grow)
+                                     : epilogue_hidden<kEpiReluSigma, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
               if (t == 0) sig0 = sig; else sig1 = sig;
             } else if (l == 8) {
-              epilogue_hidden<kEpiLinear, kTap>(cst, l, d_tmem, hrow, row, wg, tap_row);
+              if (save) epilogue_hidden<kEpiLinear, kTap, true>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
+              else epilogue_hidden<kEpiLinear, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
             } else {
-              epilogue_hidden<kEpiRelu, kTap>(cst, l, d_tmem, hrow, row, wg, tap_row);
+              if (save) epilogue_hidden<kEpiRelu, kTap, true>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
+              else epilogue_hidden<kEpiRelu, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
             }
             fence_proxy_async_smem();            // my smem writes -> visible to the next layer's UMMA
           } else {
@@ -356,15 +339,18 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + col + j));
-                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                float dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float hv = fmaxf(__uint_as_float(v[j + q]) + dd[q], 0.f);       // nerf_model.py:68-70
                   if (kTap && tap_row) tap_row[col + j + q] = hv;
+                  dd[q] = hv;
                   r = fmaf(hv, cst.w_rgb[0][col + j + q], r);                            // :74
                   g = fmaf(hv, cst.w_rgb[1][col + j + q], g);
                   b = fmaf(hv, cst.w_rgb[2][col + j + q], b);
                 }
+                if (kTrain && args.hv_out != nullptr && p < P)      // post-ReLU views hidden, for the backward
+                  *reinterpret_cast<float4*>(args.hv_out + p * kViewHidden + col + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
               }
             }
             // combine the two column halves through the (now dead) activation tile, then store
@@ -435,8 +421,10 @@ __global__ void pack_dir_kernel(const float* __restrict__ wv, float* __restrict_
   }
 }
 
-int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
-  // state_dict order: pts.{0..7}.{w,b} (0..15), views.{w,b} (16,17), feature (18,19), alpha (20,21), rgb (22,23)
+// Device-side part of packing (no host synchronisation): swizzled bf16 K-block images, the transposed
+// fp32 view-direction weights and the views bias.  t: 24 device pointers in state_dict order:
+// pts.{0..7}.{w,b} (0..15), views.{w,b} (16,17), feature (18,19), alpha (20,21), rgb (22,23).
+int pack_network_images(PackedNet& net, const float* const* t, cudaStream_t st) {
   if (!net.wimg) NWX_CUDA_TRY(cudaMalloc(&net.wimg, kWeightImageBytes));
   if (!net.wdir_t) NWX_CUDA_TRY(cudaMalloc(&net.wdir_t, sizeof(float) * kPeDir * kViewHidden));
   if (!net.bview) NWX_CUDA_TRY(cudaMalloc(&net.bview, sizeof(float) * kViewHidden));
@@ -449,6 +437,12 @@ int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
   pack_dir_kernel<<<4, 256, 0, st>>>(t[16], net.wdir_t);
   NWX_LAUNCHED();
   NWX_CUDA_TRY(cudaMemcpyAsync(net.bview, t[17], sizeof(float) * kViewHidden, cudaMemcpyDeviceToDevice, st));
+  return NWX_OK;
+}
+
+int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
+  int rc = pack_network_images(net, t, st);
+  if (rc) return rc;
   MlpConsts& c = net.consts;
   for (int i = 0; i < 8; ++i)
     NWX_CUDA_TRY(cudaMemcpyAsync(c.bias[i], t[2 * i + 1], sizeof(float) * kHidden, cudaMemcpyDeviceToHost, st));
@@ -507,16 +501,17 @@ int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t 
   return NWX_OK;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false>
 static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   using Lay = SmemLayout<kPair, kStages>;
-  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap>;
+  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain>;
   static bool configured = false;
   if (!configured) {
     NWX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
     configured = true;
   }
   const int64_t tiles = (args.P + kTileM - 1) / kTileM;
+  args.n_tiles = tiles;
   int ctas = num_sms();
   if (kPair) ctas &= ~1;
   const int units = kPair ? ctas / 2 : ctas;
@@ -555,6 +550,14 @@ int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st)
     case 3: return tap ? launch_variant<false, false, 2, true>(net, args, st) : launch_variant<false, false, 2, false>(net, args, st);
     default: return NWX_E_INVALID;
   }
+}
+
+// Training forward: same kernel (CTA pair, resident weights), biases/heads read from device memory
+// (they change every step), tensor-core operands saved as tile images for the backward.
+int launch_mlp_train_forward(const PackedNet& net, MlpArgs args, cudaStream_t st) {
+  if (args.P <= 0) return NWX_OK;
+  args.gconsts = net.gconsts;
+  return launch_variant<true, true, 4, false, true>(net, args, st);
 }
 
 }  // namespace nwx

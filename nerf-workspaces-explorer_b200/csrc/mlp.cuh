@@ -33,12 +33,33 @@ struct MlpConsts {
   float b_rgb[3];
 };
 
+// ---- training: activation / gradient tile images in HBM -------------------------------------
+// The training forward saves every tensor-core operand as the very [128 points x 64 features]
+// bf16 swizzled tile images it builds in shared memory (16 KB each), slot-major:
+//   address(slot, tile, kb) = base + ((slot_kb0(slot) * n_tiles + tile * slot_nkb(slot) + kb) << 14)
+// act slots: 0 = PE (1 K-block), 1..8 = h1..h8 (post-ReLU), 9 = feature output (pre views layer).
+// grad slots (written by the dX kernel): 0 = G_views (2 K-blocks), 1 = d_feature, 2..9 = G8..G1
+// (G_l = dL/d(pre-activation of the layer that produced h_l)).
+constexpr int kTileImgBytes = 16384;
+__host__ __device__ constexpr int act_slot_nkb(int s) { return s == 0 ? 1 : 4; }
+__host__ __device__ constexpr int act_slot_kb0(int s) { return s == 0 ? 0 : 1 + 4 * (s - 1); }
+constexpr int kActKBlocksPerTile = 37;
+__host__ __device__ constexpr int grad_slot_nkb(int s) { return s == 0 ? 2 : 4; }
+__host__ __device__ constexpr int grad_slot_kb0(int s) { return s == 0 ? 0 : 2 + 4 * (s - 1); }
+constexpr int kGradKBlocksPerTile = 38;
+__host__ __device__ inline size_t tile_img_offset(int kb0, int nkb, int64_t n_tiles, int64_t tile, int kb) {
+  return ((size_t)kb0 * n_tiles + (size_t)tile * nkb + kb) * kTileImgBytes;
+}
+
 struct PackedNet {
   uint8_t* wimg = nullptr;           // device: swizzled bf16 K-block images (kWeightImageBytes)
   float* wdir_t = nullptr;           // device: [27][128] fp32 = _views_linears.0.weight[:, 256:]^T
   float* bview = nullptr;            // device: [128] fp32 _views_linears.0.bias
   MlpConsts consts;                  // host copy
+  MlpConsts* gconsts = nullptr;      // device copy (training kernels read it through a pointer)
+  uint8_t* wimg_t = nullptr;         // device: transposed-weight K-block images for the dX kernel
   bool loaded = false;
+  bool consts_stale = false;         // host consts older than the device master weights (training)
 };
 
 struct MlpArgs {
@@ -51,13 +72,44 @@ struct MlpArgs {
   float* raw_out;                    // [P, 4]
   float* dbg_out;                    // optional tap [P, 256] (post-activation fp32 of dbg_layer)
   uint32_t* diag;                    // optional host-mapped diagnostics word(s)
+  const MlpConsts* gconsts;          // training: biases / heads read from device memory
+  uint8_t* acts;                     // training: activation tile images (see act slots), or nullptr
+  float* hv_out;                     // training: views-layer hidden [P,128] fp32 (post-ReLU), or nullptr
   int64_t P;                         // total points
-  int ray_dim, S, iters, dbg_layer;
+  int64_t n_tiles;                   // ceil(P / 128)
+  int ray_dim, S, iters, dbg_layer, which;
 };
 
 int pack_network(PackedNet& net, const float* const* tensors, cudaStream_t st);
+int pack_network_images(PackedNet& net, const float* const* tensors, cudaStream_t st);
 int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, float* out,
                    cudaStream_t st);
 int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st);
+int launch_mlp_train_forward(const PackedNet& net, MlpArgs args, cudaStream_t st);
+
+// ---- training (train.cu) ----
+struct TrainBwdArgs {
+  const float* d_raw;        // [P,4]
+  const float* hv;           // [P,128]
+  const uint8_t* acts;       // activation images of this network's forward
+  uint8_t* gimg;             // gradient image scratch (grad_image_bytes)
+  float* partial;            // [max_partials][NWX_PARAMS_PER_NET] dW partials (zero-initialised once)
+  const float* pe_dir;       // [n_rays,27] embedded view directions
+  float* grad;               // flat gradient buffer of this network (accumulated into)
+  uint32_t* diag;
+  int64_t P;
+  int S, max_partials, which;
+};
+int upload_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);       // backward kernels (train.cu)
+int upload_fwd_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);   // training forward (mlp.cu)
+size_t act_image_bytes(int64_t n_tiles);
+size_t grad_image_bytes(int64_t n_tiles);
+const int* flat_offsets();
+int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st);
+int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st);
+int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int64_t n_rays, float* d_c, float* d_f,
+                    double* loss_out, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                int step, float grad_scale, cudaStream_t st);
 
 }  // namespace nwx

@@ -63,4 +63,8 @@ inline int num_sms() {
   return n;
 }
 
+// Embedding.embed on rows of stride x_stride (rays.cu)
+int launch_embed(const float* x, int x_stride, int64_t P, int num_freqs, float scalar_factor, float* out,
+                 cudaStream_t st);
+
 }  // namespace nwx

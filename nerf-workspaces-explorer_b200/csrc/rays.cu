@@ -91,14 +91,14 @@ to8b_kernel(const float* __restrict__ x, int64_t n, uint8_t* __restrict__ out) {
 // Embedding.embed (embedding.py:44-48) for callers that want the encoding materialised; the
 // render path never does (the MLP kernel generates the features in registers).
 __global__ void __launch_bounds__(256)
-embed_kernel(const float* __restrict__ x, int64_t P, int L, float scale, float* __restrict__ out) {
+embed_kernel(const float* __restrict__ x, int x_stride, int64_t P, int L, float scale, float* __restrict__ out) {
   const int dim = 3 + 6 * L;
   const int64_t total = P * dim, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t p = i / dim;
     const int c = (int)(i - p * dim);
     const int a = c < 3 ? c : (c - 3) % 3;
-    const float xs = __fdiv_rn(__ldg(x + p * 3 + a), scale);
+    const float xs = __fdiv_rn(__ldg(x + p * x_stride + a), scale);
     float v = xs;
     if (c >= 3) {
       const int k = (c - 3) / 6;
@@ -109,17 +109,22 @@ embed_kernel(const float* __restrict__ x, int64_t P, int L, float scale, float* 
   }
 }
 
+int launch_embed(const float* x, int x_stride, int64_t P, int num_freqs, float scalar_factor, float* out,
+                 cudaStream_t st) {
+  if (P == 0) return NWX_OK;
+  int64_t blocks = (P * (3 + 6 * num_freqs) + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  embed_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, x_stride, P, num_freqs, scalar_factor, out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
 }  // namespace nwx
 
 extern "C" int nwx_embed(const float* x, int64_t P, int num_freqs, float scalar_factor, float* out, void* stream) {
   NWX_REQUIRE(x && out && P >= 0 && num_freqs >= 0 && num_freqs <= 16 && scalar_factor != 0.0f);
-  if (P == 0) return NWX_OK;
-  int64_t blocks = (P * (3 + 6 * num_freqs) + 255) / 256;
-  const int64_t cap = (int64_t)nwx::num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  nwx::embed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, P, num_freqs, scalar_factor, out);
-  NWX_LAUNCHED();
-  return NWX_OK;
+  return nwx::launch_embed(x, 3, P, num_freqs, scalar_factor, out, (cudaStream_t)stream);
 }
 
 extern "C" int nwx_raygen(const float* c2w, int B, int H, int W, float fx, float fy, float cx, float cy,

@@ -1,0 +1,774 @@
+// Training backward of the fused NeRF MLP (reference: autograd through NeRFModel.forward,
+// nerf/models/nerf_model.py:45-83, as driven by training handler:277-315) and the small kernels
+// of the optimisation step (MSE loss gradient, head gradients, Adam).
+//
+// The training forward (mlp.cu, kTrain) leaves every tensor-core operand in HBM as the same
+// [128 points x 64 features] bf16 swizzled tile images it built in shared memory.  Backward:
+//
+//   dX kernel  (mlp_bwd_dx_kernel): same persistent CTA-pair / two-tiles-in-flight skeleton as the
+//       forward.  Per tile it walks the layers backwards: G_views from the rgb head (CUDA cores),
+//       then 9 tcgen05 GEMM steps  dH_in = G_out . W  with transposed-weight K-block images streamed
+//       by bulk TMA; each epilogue applies the ReLU mask read from the saved activation image
+//       and writes the new G tile to smem (next step's A operand) and to HBM (for dW).
+//   dW kernel  (mlp_bwd_dw_kernel): layer-major.  dW[out,in] = sum_points G[p,out] X[p,in] has the
+//       points as the reduction dimension, which is the ROW dimension of the saved images, so both
+//       operands are fed to tcgen05.mma as MN-major tiles (same bytes, a_major = b_major = 1): no
+//       transposes anywhere.  Each CTA accumulates a full dW in TMEM (2 x [128 x 256] fp32) over its
+//       share of the tiles and writes one partial; bias gradients are column sums of the G tiles
+//       taken from shared memory by otherwise idle warps.  A small kernel reduces the partials.
+//   head_grads_kernel: rgb / sigma heads and the 27 view-direction columns of the views layer (fp32).
+#include "mlp_device.cuh"
+
+namespace nwx {
+
+// ------------------------------------------------------------------------------------------------
+// transposed weight images for dX:  dH_in[p][i] = sum_o G[p][o] W[o][i]  =>  B[n=i][k=o] = W[o][i]
+// steps: 0 = views (K = 128 -> 2 K-blocks), 1 = feature, 2..8 = pts layers 7..1 (4 K-blocks each)
+// ------------------------------------------------------------------------------------------------
+constexpr int kDxSteps = 9;
+constexpr int kDxKBlocks = 2 + 8 * 4;     // 34 images of [256 x 64]
+__host__ __device__ constexpr int dx_step_nkb(int s) { return s == 0 ? 2 : 4; }
+__host__ __device__ constexpr int dx_step_kb0(int s) { return s == 0 ? 0 : 2 + 4 * (s - 1); }
+
+struct PackTSrc {
+  const float* w[kDxSteps];   // views, feature, pts7, pts6, pts5, pts4, pts3, pts2, pts1
+};
+
+__global__ void pack_weights_t_kernel(PackTSrc src, uint8_t* __restrict__ wimg_t) {
+  const int g = blockIdx.x;
+  int s = 0, kb = g;
+  while (kb >= dx_step_nkb(s)) { kb -= dx_step_nkb(s); ++s; }
+  // source tensor [out, in_dim]; dX needs input columns c0 .. c0+255 (the h part) only
+  const int in_dim = (s == 0) ? kHidden + kPeDir : (s == 4 ? kPeXyz + kHidden : kHidden);   // s==4 is pts layer 5
+  const int c0 = (s == 4) ? kPeXyz : 0;
+  const int outs = (s == 0) ? kViewHidden : kHidden;
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(wimg_t + (size_t)g * kKBlockBytes);
+  for (int e = threadIdx.x; e < kHidden * 64; e += blockDim.x) {
+    const int n = e >> 6, c = e & 63;                 // n = input feature (row of B), c = k within the block
+    const int o = kb * 64 + c;                        // output feature = reduction index
+    const float v = (o < outs) ? src.w[s][(size_t)o * in_dim + c0 + n] : 0.0f;
+    img[n * 64 + (((c >> 3) ^ (n & 7)) << 3) + (c & 7)] = __float2bfloat16_rn(v);
+  }
+}
+
+struct TensorTable {
+  const float* t[NWX_NUM_WEIGHT_TENSORS];     // state_dict order (see pack_network_images)
+};
+
+__global__ void fill_consts_kernel(TensorTable tab, MlpConsts* __restrict__ c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 9 * kHidden) {
+    const int l = i / kHidden, j = i % kHidden;
+    c->bias[l][j] = (l < 8) ? tab.t[2 * l + 1][j] : tab.t[19][j];
+  }
+  if (i < kHidden) c->w_alpha[i] = tab.t[20][i];
+  if (i < 3 * kViewHidden) (&c->w_rgb[0][0])[i] = tab.t[22][i];
+  if (i == 0) c->b_alpha = tab.t[21][0];
+  if (i < 3) c->b_rgb[i] = tab.t[23][i];
+}
+
+// Biases and heads of the two networks for the training kernels.  They change every optimiser step,
+// so they cannot ride in the launch parameters (host copy) like at inference; a stream-ordered
+// device-to-device cudaMemcpyToSymbolAsync refreshes them and the epilogues keep reading them
+// through the constant bank (uniform LDC) instead of global loads.
+__constant__ MlpConsts c_train_consts[2];
+
+int upload_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st) {
+  NWX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_train_consts, dev_src, sizeof(MlpConsts), (size_t)which * sizeof(MlpConsts),
+                                       cudaMemcpyDeviceToDevice, st));
+  return NWX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dX kernel
+// ------------------------------------------------------------------------------------------------
+struct DxArgs {
+  const float* d_raw;        // [P,4] dL/d(raw rgb, raw sigma)
+  const float* hv;           // [P,128] views hidden (post-ReLU) saved by the forward
+  const uint8_t* acts;       // activation images (forward)
+  uint8_t* grads;            // gradient images (output)
+  const uint8_t* wimg_t;     // transposed weight images
+  const MlpConsts* gconsts;
+  uint32_t* diag;
+  int64_t P, n_tiles;
+  int iters, which;
+};
+
+enum { kBwdLinear = 0, kBwdSigmaMask = 1, kBwdMask = 2 };
+
+template <int kKind>
+__device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tmem, uint32_t hrow, bool to_smem, int row,
+                                             int wg, const uint8_t* mrow, uint8_t* grow, float dsig) {
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    const int col = wg * 128 + cc * 32;
+    const uint32_t kbo = (uint32_t)(col >> 6) * kTileImgBytes;
+    const int j0 = (col & 63) >> 3;
+    uint4 m[4];
+    if (kKind != kBwdLinear) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m[q] = __ldg(reinterpret_cast<const uint4*>(mrow + kbo + (((j0 + q) ^ (row & 7)) << 4)));
+    }
+    uint32_t v[32];
+    tmem_ld32(d_tmem + col, v);
+    tmem_wait_ld();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+      if (kKind == kBwdSigmaMask) {                 // d h8 += dsigma * w_alpha (sigma head, nerf_model.py:63)
+        a = fmaf(dsig, cst.w_alpha[col + j], a);
+        b = fmaf(dsig, cst.w_alpha[col + j + 1], b);
+      }
+      if (kKind != kBwdLinear) {                    // ReLU': the saved activation is > 0
+        const uint32_t mw = (&m[j >> 3].x)[(j & 7) >> 1];
+        a = (mw & 0xFFFFu) ? a : 0.0f;
+        b = (mw >> 16) ? b : 0.0f;
+      }
+      pk[j >> 1] = pack_bf16x2(a, b);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t off = kbo + (((j0 + q) ^ (row & 7)) << 4);
+      if (to_smem) st_shared_v4(hrow + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
+  constexpr int kStages = 4;
+  using L = SmemLayout<true, kStages>;
+  const MlpConsts& cst = c_train_consts[args.which];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int units = gridDim.x / 2, unit = blockIdx.x / 2;
+  const int64_t P = args.P;
+  const int iters = args.iters;
+  auto tile_of = [&](int it, int t) -> int64_t { return (((int64_t)it * units + unit) * 2 + t) * 2 + rank; };
+  auto leader = [&](uint32_t local) -> uint32_t { return mapa(local, 0); };
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(sbase + L::w_full + 8 * s, 1);
+      mbar_init(sbase + L::w_empty + 8 * s, 1);
+      mbar_init(sbase + L::w_peer + 8 * s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(sbase + L::acc_full + 8 * t, 1);
+      mbar_init(sbase + L::a_ready + 8 * t, 16);
+      mbar_init(sbase + L::pe_ready + 8 * t, 8);
+      mbar_init(sbase + L::pe_free + 8 * t, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<2>(sbase + L::tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (sbase - smem_u32(smem_raw)) + L::tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {                                           // ---- TMA producer: transposed weights
+      const WaitCtx wc{args.diag, 0x1100u};
+      uint32_t fill = 0;
+      const uint32_t bytes = kKBlockBytes / 2;
+      for (int it = 0; it < iters; ++it)
+        for (int s = 0; s < kDxSteps; ++s)
+          for (int kb = 0; kb < dx_step_nkb(s); ++kb, ++fill) {
+            const uint32_t stage = fill % kStages, round = fill / kStages;
+            mbar_wait(sbase + L::w_empty + 8 * stage, (round & 1) ^ 1, wc);
+            const uint32_t bar = sbase + L::w_full + 8 * stage;
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s(sbase + L::w0 + stage * L::kStageBytes,
+                     args.wimg_t + (size_t)(dx_step_kb0(s) + kb) * kKBlockBytes + rank * bytes, bytes, bar);
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                           // ---- MMA issuer / relay
+      const WaitCtx wc{args.diag, 0x1200u};
+      uint32_t fill = 0;
+      if (rank == 0) {
+        const uint32_t idesc = umma_idesc_bf16(256, kHidden);
+        for (int it = 0; it < iters; ++it) {
+          for (int s = 0; s < kDxSteps; ++s) {
+            const int nkb = dx_step_nkb(s);
+            for (int t = 0; t < 2; ++t) {
+              if (s == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
+              // a_ready[t] completes once per step epilogue: phase index = 9*it + s - 1
+              if (s != 0 || it != 0) mbar_wait(sbase + L::a_ready + 8 * t, (9 * it + s + 1) & 1, wc);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + t * kHidden;
+              for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t f = fill + kb;
+                const uint32_t stage = f % kStages, round = f / kStages;
+                if (t == 0) {
+                  mbar_wait(sbase + L::w_full + 8 * stage, round & 1, wc);
+                  mbar_wait(sbase + L::w_peer + 8 * stage, round & 1, wc);
+                  tc_fence_after();
+                }
+                const uint64_t adesc = umma_desc_k_sw128(sbase + L::h0 + t * kHBytes + kb * kABlock);
+                const uint64_t bdesc = umma_desc_k_sw128(sbase + L::w0 + stage * L::kStageBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16<2>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                if (t == 1) umma_commit<2>(sbase + L::w_empty + 8 * stage);
+              }
+              umma_commit<2>(sbase + L::acc_full + 8 * t);
+              if (s == kDxSteps - 1) umma_commit<2>(sbase + L::pe_free + 8 * t);   // tile buffer free for the next G_views
+            }
+            fill += nkb;
+          }
+        }
+      } else {
+        for (uint32_t n = 0; n < (uint32_t)kDxKBlocks * (uint32_t)iters; ++n, ++fill) {
+          const uint32_t stage = fill % kStages, round = fill / kStages;
+          mbar_wait(sbase + L::w_full + 8 * stage, round & 1, wc);
+          mbar_arrive_cluster(mapa(sbase + L::w_peer + 8 * stage, 0));
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---- G_views producers: g_v = (W_rgb^T d_rgb) * [hv > 0]   (rgb head + views ReLU backward)
+    const WaitCtx wc{args.diag, 0x1300u};
+    const int row = (warp - 4) * 32 + lane;
+    for (int it = 0; it < iters; ++it) {
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = tile_of(it, t);
+        const int64_t p = tile * kTileM + row;
+        const bool live = p < P;
+        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) dr = __ldg(reinterpret_cast<const float4*>(args.d_raw) + p);
+        if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
+        const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
+        uint8_t* grow = (tile < args.n_tiles)
+                            ? args.grads + tile_img_offset(grad_slot_kb0(0), 2, args.n_tiles + 1, tile, 0) + row * 128 : nullptr;
+#pragma unroll 1
+        for (int c8 = 0; c8 < 16; ++c8) {                       // 16 chunks of 8 columns = 128 columns
+          float hvv[8];
+          if (live) {
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(args.hv + p * kViewHidden + c8 * 8));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(args.hv + p * kViewHidden + c8 * 8 + 4));
+            hvv[0] = h0.x; hvv[1] = h0.y; hvv[2] = h0.z; hvv[3] = h0.w;
+            hvv[4] = h1.x; hvv[5] = h1.y; hvv[6] = h1.z; hvv[7] = h1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hvv[e] = 0.f;
+          }
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float g[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = c8 * 8 + e + h;
+              const float v = fmaf(cst.w_rgb[0][j], dr.x, fmaf(cst.w_rgb[1][j], dr.y, cst.w_rgb[2][j] * dr.z));
+              g[h] = hvv[e + h] > 0.f ? v : 0.f;
+            }
+            pk[e >> 1] = pack_bf16x2(g[0], g[1]);
+          }
+          const uint32_t off = (uint32_t)(c8 >> 3) * kTileImgBytes + (((c8 & 7) ^ (row & 7)) << 4);
+          st_shared_v4(hrow + off, pk[0], pk[1], pk[2], pk[3]);
+          if (grow) *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader(sbase + L::pe_ready + 8 * t));
+      }
+    }
+  } else if (warp >= 8) {
+    // ---- epilogues
+    const WaitCtx wc{args.diag, 0x1400u};
+    const int quad = warp & 3, wg = (warp - 8) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int it = 0; it < iters; ++it) {
+      float dsig[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t p = tile_of(it, t) * kTileM + row;
+        dsig[t] = (p < P) ? __ldg(args.d_raw + p * 4 + 3) : 0.f;
+      }
+      for (int s = 0; s < kDxSteps; ++s) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(sbase + L::acc_full + 8 * t, (9 * it + s) & 1, wc);
+          tc_fence_after();
+          const int64_t tile = tile_of(it, t);
+          // dead tiles (past the end) still run so the barrier protocol stays uniform; they write
+          // to a scratch tile at the very end of the gradient image buffer
+          const int64_t wt = tile < args.n_tiles ? tile : args.n_tiles;
+          const uint32_t d_tmem = lane_addr + t * kHidden;
+          const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
+          uint8_t* grow = args.grads + tile_img_offset(grad_slot_kb0(s + 1), 4, args.n_tiles + 1, wt, 0) + row * 128;
+          // mask = activation that the produced gradient flows into: step 1 -> h8 (act slot 8) ... step 8 -> h1
+          const int64_t mt = tile < args.n_tiles ? tile : 0;
+          const uint8_t* mrow = args.acts + tile_img_offset(act_slot_kb0(s == 0 ? 9 : 9 - s), 4, args.n_tiles, mt, 0) + row * 128;
+          if (s == 0) bwd_epilogue<kBwdLinear>(cst, d_tmem, hrow, true, row, wg, mrow, grow, 0.f);
+          else if (s == 1) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, row, wg, mrow, grow, dsig[t]);
+          else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, row, wg, mrow, grow, 0.f);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dW kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwJobs = 11;
+struct DwJob {
+  int g_kb0, g_nkb;          // gradient image slot (K-block offset, count): out features = 64 * g_nkb
+  int x_kb0, x_nkb;          // activation image slot: in features = 64 * x_nkb (n_valid of them real)
+  int w_off, in_stride, col0, n_valid;   // where dW[out][col0 + c] goes in the flat gradient buffer
+  int b_off;                 // bias gradient offset, or -1 (second job on the same G)
+};
+struct DwArgs {
+  const uint8_t* acts;
+  const uint8_t* grads;
+  float* partial;            // [gridDim.x][NWX_PARAMS_PER_NET]
+  uint32_t* diag;
+  int64_t n_tiles;
+  DwJob job[kDwJobs];
+};
+
+constexpr int kDwStages = 3;
+constexpr uint32_t kDwStageBytes = 65536;        // 64 points: G 4 x 8 KB | X 4 x 8 KB
+struct DwSmem {
+  static constexpr uint32_t stage0 = 0;
+  static constexpr uint32_t full = kDwStages * kDwStageBytes;      // barriers
+  static constexpr uint32_t empty = full + 8 * kDwStages;
+  static constexpr uint32_t acc_full = empty + 8 * kDwStages;
+  static constexpr uint32_t acc_free = acc_full + 8;
+  static constexpr uint32_t tmem_slot = acc_free + 8;
+  static constexpr uint32_t total = tmem_slot + 16;
+  static constexpr uint32_t alloc_bytes = total + 1024;
+};
+
+// MN-major operand descriptor, SWIZZLE_128B: 64 contiguous MN elements (128 B) x 8 K rows per atom;
+// LBO = byte distance between 64-element MN blocks, SBO = byte distance between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);     // a_major = b_major = MN
+}
+
+__global__ void __launch_bounds__(512, 1)
+mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
+  using S = DwSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = args.n_tiles;
+  // my tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kDwStages; ++s) {
+      mbar_init(sbase + S::full + 8 * s, 1);
+      mbar_init(sbase + S::empty + 8 * s, 2);        // MMA commit + bias reducers
+    }
+    mbar_init(sbase + S::acc_full, 1);
+    mbar_init(sbase + S::acc_free, 4);               // one per flush warp
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(sbase + S::tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + S::tmem_slot);
+  float* partial = args.partial + (size_t)blockIdx.x * NWX_PARAMS_PER_NET;
+
+  if (warp == 0) {
+    if (lane == 0) {                                           // ---- producer: 64-point half tiles of G and X
+      const WaitCtx wc{args.diag, 0x2100u};
+      uint32_t fill = 0;
+      for (int j = 0; j < kDwJobs; ++j) {
+        const DwJob jb = args.job[j];
+        const uint32_t bytes = (uint32_t)(jb.g_nkb + jb.x_nkb) * 8192u;
+        for (int i = 0; i < my_tiles; ++i) {
+          const int64_t tile = blockIdx.x + (int64_t)i * gridDim.x;
+          for (int half = 0; half < 2; ++half, ++fill) {
+            const uint32_t stage = fill % kDwStages, round = fill / kDwStages;
+            mbar_wait(sbase + S::empty + 8 * stage, (round & 1) ^ 1, wc);
+            const uint32_t bar = sbase + S::full + 8 * stage;
+            mbar_arrive_expect_tx(bar, bytes);
+            const uint32_t dst = sbase + S::stage0 + stage * kDwStageBytes;
+            for (int kb = 0; kb < jb.g_nkb; ++kb)
+              bulk_g2s(dst + kb * 8192, args.grads + tile_img_offset(jb.g_kb0, jb.g_nkb, n_tiles + 1, tile, kb) + half * 8192,
+                       8192, bar);
+            for (int kb = 0; kb < jb.x_nkb; ++kb)
+              bulk_g2s(dst + 32768 + kb * 8192, args.acts + tile_img_offset(jb.x_kb0, jb.x_nkb, n_tiles, tile, kb) + half * 8192,
+                       8192, bar);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                           // ---- MMA issuer
+      const WaitCtx wc{args.diag, 0x2200u};
+      uint32_t fill = 0;
+      for (int j = 0; j < kDwJobs; ++j) {
+        const DwJob jb = args.job[j];
+        const int mhalves = jb.g_nkb / 2;
+        const uint32_t idesc = umma_idesc_bf16_mn(128, 64 * jb.x_nkb);
+        if (j > 0) mbar_wait(sbase + S::acc_free, (j - 1) & 1, wc);      // previous dW flushed out of TMEM
+        tc_fence_after();
+        for (int i = 0; i < 2 * my_tiles; ++i, ++fill) {
+          const uint32_t stage = fill % kDwStages, round = fill / kDwStages;
+          mbar_wait(sbase + S::full + 8 * stage, round & 1, wc);
+          tc_fence_after();
+          const uint32_t st = sbase + S::stage0 + stage * kDwStageBytes;
+          for (int mh = 0; mh < mhalves; ++mh) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                      // 4 x 16 points; 16 rows = 2048 B
+              const uint64_t adesc = umma_desc_mn_sw128(st + mh * 16384 + k * 2048, 8192, 1024);
+              const uint64_t bdesc = umma_desc_mn_sw128(st + 32768 + k * 2048, 8192, 1024);
+              umma_bf16<1>(tmem_base + mh * 256, adesc, bdesc, idesc, (i | k) != 0);
+            }
+          }
+          umma_commit<1>(sbase + S::empty + 8 * stage);
+        }
+        umma_commit<1>(sbase + S::acc_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---- flush: TMEM dW (lane = output feature) -> this CTA's partial
+    const WaitCtx wc{args.diag, 0x2300u};
+    const int quad = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int j = 0; j < kDwJobs; ++j) {
+      const DwJob jb = args.job[j];
+      mbar_wait(sbase + S::acc_full, j & 1, wc);
+      tc_fence_after();
+      for (int mh = 0; mh < jb.g_nkb / 2; ++mh) {
+        const int o = mh * 128 + quad * 32 + lane;
+        float* dst = partial + jb.w_off + (size_t)o * jb.in_stride + jb.col0;
+        for (int c0 = 0; c0 < 64 * jb.x_nkb; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + mh * 256 + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c0 + c < jb.n_valid) dst[c0 + c] = __uint_as_float(v[c]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sbase + S::acc_free);
+    }
+  } else if (warp >= 8) {
+    // ---- bias gradients: column sums of the G half-tiles, straight from shared memory
+    const WaitCtx wc{args.diag, 0x2400u};
+    const int c = threadIdx.x - 256;                 // column 0..255
+    uint32_t fill = 0;
+    for (int j = 0; j < kDwJobs; ++j) {
+      const DwJob jb = args.job[j];
+      const bool mine = jb.b_off >= 0 && c < 64 * jb.g_nkb;
+      float acc = 0.f;
+      for (int i = 0; i < 2 * my_tiles; ++i, ++fill) {
+        const uint32_t stage = fill % kDwStages, round = fill / kDwStages;
+        mbar_wait(sbase + S::full + 8 * stage, round & 1, wc);
+        if (mine) {
+          const uint8_t* blk = sgen + S::stage0 + stage * kDwStageBytes + (c >> 6) * 8192 + (c & 7) * 2;
+          const int ch = (c & 63) >> 3;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r)
+            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
+        }
+        named_bar_sync(2, 256);                      // all 8 reducer warps done with this stage
+        if (threadIdx.x == 256) mbar_arrive(sbase + S::empty + 8 * stage);
+      }
+      if (mine) partial[jb.b_off + c] = acc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// grad[i] += sum over CTAs of partial[cta][i]
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int n_parts, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NWX_PARAMS_PER_NET) return;
+  float s = 0.f;
+  for (int c = 0; c < n_parts; ++c) s += partial[(size_t)c * NWX_PARAMS_PER_NET + i];
+  grad[i] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads: rgb (3x128), sigma (1x256) and the 27 view-direction columns of the views layer -- fp32
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadTiles = 4;      // tiles (of 128 points) per block of head_grads_kernel
+struct HeadArgs {
+  const float* d_raw;        // [P,4]
+  const float* hv;           // [P,128]
+  const uint8_t* acts;       // h8 images (act slot 8)
+  const float* pe_dir;       // [n_rays, 27]
+  const MlpConsts* gconsts;
+  float* grad;               // flat gradient buffer of the net (atomics)
+  int64_t P, n_tiles;
+  int S;
+  int off_wv, off_walpha, off_balpha, off_wrgb, off_brgb;
+};
+
+__global__ void __launch_bounds__(256)
+head_grads_kernel(const HeadArgs a) {
+  // threads 0..127: one views-hidden column each (rgb head, view-direction columns of the views
+  // layer); threads 128..255: two h8 columns each (sigma head).  A block owns kHeadTiles
+  // consecutive tiles, accumulates in registers and finishes with one atomicAdd per output.
+  const int tid = threadIdx.x;
+  const MlpConsts& cst = *a.gconsts;
+  float wr[3] = {0.f, 0.f, 0.f}, d_wr[3] = {0.f, 0.f, 0.f}, d_dir[kPeDir];
+  float d_wa[2] = {0.f, 0.f}, d_b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < kPeDir; ++i) d_dir[i] = 0.f;
+  if (tid < kViewHidden) { wr[0] = cst.w_rgb[0][tid]; wr[1] = cst.w_rgb[1][tid]; wr[2] = cst.w_rgb[2][tid]; }
+  const int64_t tile0 = (int64_t)blockIdx.x * kHeadTiles;
+  for (int64_t tile = tile0; tile < tile0 + kHeadTiles && tile < a.n_tiles; ++tile) {
+    const int64_t p0 = tile * kTileM;
+    const int n = (int)((a.P - p0) < kTileM ? (a.P - p0) : kTileM);
+    if (tid < kViewHidden) {
+      float gsum = 0.f;
+      int64_t ray = p0 / a.S;
+      for (int r0 = 0; r0 < n; r0 += 8) {
+        float4 d[8];
+        float h[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                           // 8 points in flight: all loads first
+          const int64_t p = p0 + ((r0 + q < n) ? r0 + q : n - 1);
+          d[q] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + p);
+          h[q] = __ldg(a.hv + p * kViewHidden + tid);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (r0 + q >= n) break;
+          const int64_t pr = (p0 + r0 + q) / a.S;
+          if (pr != ray) {                                      // ray boundary: fold the ray's sum of g_v
+#pragma unroll
+            for (int i = 0; i < kPeDir; ++i) d_dir[i] = fmaf(gsum, __ldg(a.pe_dir + ray * kPeDir + i), d_dir[i]);
+            gsum = 0.f; ray = pr;
+          }
+          d_wr[0] = fmaf(d[q].x, h[q], d_wr[0]); d_wr[1] = fmaf(d[q].y, h[q], d_wr[1]); d_wr[2] = fmaf(d[q].z, h[q], d_wr[2]);
+          if (h[q] > 0.f) gsum += fmaf(wr[0], d[q].x, fmaf(wr[1], d[q].y, wr[2] * d[q].z));
+          if (tid == 0) { d_b[0] += d[q].x; d_b[1] += d[q].y; d_b[2] += d[q].z; d_b[3] += d[q].w; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kPeDir; ++i) d_dir[i] = fmaf(gsum, __ldg(a.pe_dir + ray * kPeDir + i), d_dir[i]);
+    } else {
+      const int c0 = (tid - kViewHidden) * 2;                  // two h8 columns per thread
+      const uint8_t* img = a.acts + tile_img_offset(act_slot_kb0(8), 4, a.n_tiles, tile, c0 >> 6) + (c0 & 7) * 2;
+      const int ch = (c0 & 63) >> 3;
+      for (int r0 = 0; r0 < n; r0 += 8) {
+        float ds[8];
+        uint32_t hh[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = (r0 + q < n) ? r0 + q : n - 1;
+          ds[q] = (r0 + q < n) ? __ldg(a.d_raw + (p0 + r) * 4 + 3) : 0.f;
+          hh[q] = *reinterpret_cast<const uint32_t*>(img + r * 128 + ((ch ^ (r & 7)) << 4));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          d_wa[0] = fmaf(ds[q], __uint_as_float(hh[q] << 16), d_wa[0]);
+          d_wa[1] = fmaf(ds[q], __uint_as_float(hh[q] & 0xFFFF0000u), d_wa[1]);
+        }
+      }
+    }
+  }
+  if (tid < kViewHidden) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(a.grad + a.off_wrgb + c * kViewHidden + tid, d_wr[c]);
+#pragma unroll
+    for (int i = 0; i < kPeDir; ++i) atomicAdd(a.grad + a.off_wv + tid * (kHidden + kPeDir) + kHidden + i, d_dir[i]);
+    if (tid == 0) {
+      for (int c = 0; c < 3; ++c) atomicAdd(a.grad + a.off_brgb + c, d_b[c]);
+      atomicAdd(a.grad + a.off_balpha, d_b[3]);
+    }
+  } else {
+    const int c0 = (tid - kViewHidden) * 2;
+    atomicAdd(a.grad + a.off_walpha + c0, d_wa[0]);
+    atomicAdd(a.grad + a.off_walpha + c0 + 1, d_wa[1]);
+  }
+}
+
+// d(loss)/d(rgb) for loss = mean((rgb_c - gt)^2) + mean((rgb_f - gt)^2)  (training handler:291-305);
+// loss_out[0..1] accumulate the two MSE terms (double, like the reference's fp64 loss).
+__global__ void __launch_bounds__(256)
+mse_grad_kernel(const float* __restrict__ rgb_c, const float* __restrict__ rgb_f, const float* __restrict__ gt,
+                int64_t n3, float* __restrict__ d_c, float* __restrict__ d_f, double* __restrict__ loss_out) {
+  double lc = 0.0, lf = 0.0;
+  const float scale = 2.0f / (float)n3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = gt[i], ec = rgb_c[i] - g, ef = rgb_f[i] - g;
+    d_c[i] = scale * ec; d_f[i] = scale * ef;
+    lc += (double)ec * ec; lf += (double)ef * ef;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lc += __shfl_xor_sync(kFull, lc, o); lf += __shfl_xor_sync(kFull, lf, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(loss_out, lc / (double)n3); atomicAdd(loss_out + 1, lf / (double)n3); }
+}
+
+// torch.optim.Adam, default betas/eps, no weight decay (training handler:234); g is pre-scaled by grad_scale.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale) {
+  const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// offsets of the 24 tensors in the flat state_dict-ordered parameter / gradient buffer
+struct FlatLayout {
+  int off[NWX_NUM_WEIGHT_TENSORS];
+  FlatLayout() {
+    const int sizes[NWX_NUM_WEIGHT_TENSORS] = {
+        256 * 63, 256, 256 * 256, 256, 256 * 256, 256, 256 * 256, 256, 256 * 256, 256, 256 * 319, 256,
+        256 * 256, 256, 256 * 256, 256, 128 * 283, 128, 256 * 256, 256, 256, 1, 3 * 128, 3};
+    int o = 0;
+    for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) { off[i] = o; o += sizes[i]; }
+  }
+};
+static const FlatLayout g_flat;
+
+const int* flat_offsets() { return g_flat.off; }
+
+// Re-pack one network from its flat fp32 master parameters (state_dict order): forward images,
+// transposed images for dX, device-side biases/heads.  Stream-ordered, no host synchronisation,
+// so it can follow the optimiser step directly.
+int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st) {
+  if (!net.wimg_t) NWX_CUDA_TRY(cudaMalloc(&net.wimg_t, (size_t)kDxKBlocks * kKBlockBytes));
+  if (!net.gconsts) NWX_CUDA_TRY(cudaMalloc(&net.gconsts, sizeof(MlpConsts)));
+  TensorTable tab;
+  for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) tab.t[i] = params_flat + g_flat.off[i];
+  int rc = pack_network_images(net, tab.t, st);
+  if (rc) return rc;
+  PackTSrc ts;
+  ts.w[0] = tab.t[16];
+  ts.w[1] = tab.t[18];
+  for (int s = 2; s < kDxSteps; ++s) ts.w[s] = tab.t[2 * (9 - s)];     // pts layers 7..1
+  pack_weights_t_kernel<<<kDxKBlocks, 256, 0, st>>>(ts, net.wimg_t);
+  NWX_LAUNCHED();
+  fill_consts_kernel<<<(9 * kHidden + 255) / 256, 256, 0, st>>>(tab, net.gconsts);
+  NWX_LAUNCHED();
+  net.loaded = true;       // the training kernels are usable; the host copy of the consts is NOT refreshed
+  net.consts_stale = true;
+  return NWX_OK;
+}
+
+// ---- launchers ------------------------------------------------------------------------------------
+size_t act_image_bytes(int64_t n_tiles) { return (size_t)kActKBlocksPerTile * n_tiles * kTileImgBytes; }
+size_t grad_image_bytes(int64_t n_tiles) { return (size_t)kGradKBlocksPerTile * (n_tiles + 1) * kTileImgBytes; }
+
+// Backward of one network: d_raw [P,4] -> flat gradient buffer `grad` (state_dict order, += into it).
+int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st) {
+  if (a.P <= 0) return NWX_OK;
+  const int64_t tiles = (a.P + kTileM - 1) / kTileM;
+  // ---- dX ----
+  {
+    using Lay = SmemLayout<true, 4>;
+    static bool configured = false;
+    if (!configured) {
+      NWX_CUDA_TRY(cudaFuncSetAttribute(mlp_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
+      configured = true;
+    }
+    DxArgs d{};
+    d.d_raw = a.d_raw; d.hv = a.hv; d.acts = a.acts; d.grads = a.gimg; d.wimg_t = net.wimg_t; d.gconsts = net.gconsts;
+    d.diag = a.diag; d.P = a.P; d.n_tiles = tiles; d.which = a.which;
+    const int units = (num_sms() & ~1) / 2;
+    int64_t need = (tiles + 3) / 4;
+    const int use = (int)(need < units ? need : units);
+    d.iters = (int)((tiles + (int64_t)use * 4 - 1) / ((int64_t)use * 4));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(use * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Lay::alloc_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    NWX_CUDA_TRY(cudaLaunchKernelEx(&cfg, mlp_bwd_dx_kernel, d));
+    g_nwx_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  // ---- dW ----
+  int grid = num_sms();
+  if (grid > tiles) grid = (int)tiles;
+  if (grid > a.max_partials) grid = a.max_partials;
+  {
+    static bool configured = false;
+    if (!configured) {
+      NWX_CUDA_TRY(cudaFuncSetAttribute(mlp_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DwSmem::alloc_bytes));
+      configured = true;
+    }
+    DwArgs w{};
+    w.acts = a.acts; w.grads = a.gimg; w.partial = a.partial; w.diag = a.diag; w.n_tiles = tiles;
+    const int* off = g_flat.off;
+    auto job = [&](int j, int gslot, int aslot, int wt, int stride, int col0, int nvalid, int bt) {
+      w.job[j] = DwJob{grad_slot_kb0(gslot), grad_slot_nkb(gslot), act_slot_kb0(aslot), act_slot_nkb(aslot),
+                       off[wt], stride, col0, nvalid, bt >= 0 ? off[bt] : -1};
+    };
+    job(0, 9, 0, 0, 63, 0, 63, 1);                 // pts0: G1 x PE
+    for (int l = 1; l <= 4; ++l) job(l, 9 - l, l, 2 * l, 256, 0, 256, 2 * l + 1);   // pts1..4: G_{l+1} x h_l
+    job(5, 4, 0, 10, 319, 0, 63, 11);              // pts5, PE columns
+    job(6, 4, 5, 10, 319, 63, 256, -1);            // pts5, h5 columns
+    job(7, 3, 6, 12, 256, 0, 256, 13);             // pts6: G7 x h6
+    job(8, 2, 7, 14, 256, 0, 256, 15);             // pts7: G8 x h7
+    job(9, 1, 8, 18, 256, 0, 256, 19);             // feature: d_f x h8
+    job(10, 0, 9, 16, 283, 0, 256, 17);            // views: G_v x f
+    mlp_bwd_dw_kernel<<<grid, 512, DwSmem::alloc_bytes, st>>>(w);
+    NWX_LAUNCHED();
+  }
+  reduce_partials_kernel<<<(NWX_PARAMS_PER_NET + 255) / 256, 256, 0, st>>>(a.partial, grid, a.grad);
+  NWX_LAUNCHED();
+  HeadArgs h{};
+  h.d_raw = a.d_raw; h.hv = a.hv; h.acts = a.acts; h.pe_dir = a.pe_dir; h.gconsts = net.gconsts; h.grad = a.grad;
+  h.P = a.P; h.n_tiles = tiles; h.S = a.S;
+  h.off_wv = g_flat.off[16]; h.off_walpha = g_flat.off[20]; h.off_balpha = g_flat.off[21];
+  h.off_wrgb = g_flat.off[22]; h.off_brgb = g_flat.off[23];
+  head_grads_kernel<<<(unsigned)((tiles + kHeadTiles - 1) / kHeadTiles), 256, 0, st>>>(h);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int64_t n_rays, float* d_c, float* d_f,
+                    double* loss_out, cudaStream_t st) {
+  NWX_CUDA_TRY(cudaMemsetAsync(loss_out, 0, 2 * sizeof(double), st));
+  int64_t blocks = (n_rays * 3 + 255) / 256;
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  mse_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(rgb_c, rgb_f, gt, n_rays * 3, d_c, d_f, loss_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                int step, float grad_scale, cudaStream_t st) {
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+}  // namespace nwx

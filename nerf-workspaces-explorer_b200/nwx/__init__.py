@@ -16,5 +16,6 @@ from .inference import NeRFReplicaInferenceHandler                         # noq
 from .models import (Embedding, NeRFModel, img2mse, mse2psnr, raw2outputs, run_network,   # noqa: F401
                      to8b, to8b_np)
 from .rays import create_rays, sample_pdf                                  # noqa: F401
+from .training import NeRFReplicaTrainingHandler, Trainer                  # noqa: F401
 
 __version__ = "0.1.0"

@@ -33,6 +33,11 @@ class RenderOut(C.Structure):
     _fields_ = [(name, _vp) for name in RENDER_OUT_FIELDS]
 
 
+class TrainIO(C.Structure):
+    _fields_ = [(name, _vp) for name in ("rays", "gt_rgb", "grad_coarse", "grad_fine", "loss", "rgb_coarse",
+                                         "rgb_fine")]
+
+
 # name -> (restype, argtypes); mirrors include/nwx.h one to one
 PROTOTYPES = {
     "nwx_version": (_i, []),
@@ -51,6 +56,10 @@ PROTOTYPES = {
     "nwx_sample_pdf": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nwx_sample_pdf_bins": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "nwx_ctx_reserve": (_i, [_vp, _i64, _i, _i]),
+    "nwx_param_offsets": (_i, [C.POINTER(_i)]),
+    "nwx_train_pack": (_i, [_vp, _i, _vp, _vp]),
+    "nwx_train_fwd_bwd": (_i, [_vp, C.POINTER(TrainIO), _i64, C.POINTER(RenderOpts), _vp]),
+    "nwx_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp]),
     "nwx_ctx_set_profiling": (_i, [_vp, _i]),
     "nwx_ctx_stage_ms": (_i, [_vp, C.POINTER(_f)]),
     "nwx_render_rays": (_i, [_vp, _vp, _i64, C.POINTER(RenderOpts), C.POINTER(RenderOut), _vp]),

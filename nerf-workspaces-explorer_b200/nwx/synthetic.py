@@ -2,7 +2,7 @@
 checkpoints are not available, so benchmarks use the GUI's 36-pose sweep at a random spot of the
 office_tokyo room and random-init weights of the reference architecture."""
 import math
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -28,7 +28,7 @@ def sweep_poses(n: int = 36, seed: int = 0) -> torch.Tensor:
     return get_camera_poses_from_list_of_coordinates(init, views[:n])
 
 
-def random_state_dicts(seed: int = 0, alpha_bias: float = 0.1) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+def random_state_dicts(seed: int = 0, alpha_bias: Optional[float] = 0.1) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
     """Coarse and fine weights exactly as the reference handler would create them under
     torch.manual_seed(seed) (inference handler:106-119), with _alpha_linear.bias pinned so the
     density sign at the far sample is not a coin flip."""
@@ -37,7 +37,8 @@ def random_state_dicts(seed: int = 0, alpha_bias: float = 0.1) -> Tuple[Dict[str
         nets = [NeRFModel(8, 256, 63, 27, 5, use_view_dirs=True) for _ in range(2)]
     out = []
     for net in nets:
-        with torch.no_grad():
-            net._alpha_linear.bias.fill_(alpha_bias)
+        if alpha_bias is not None:
+            with torch.no_grad():
+                net._alpha_linear.bias.fill_(alpha_bias)
         out.append({k: v.detach().clone() for k, v in net.state_dict().items()})
     return out[0], out[1]

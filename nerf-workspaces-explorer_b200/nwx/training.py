@@ -1,0 +1,171 @@
+"""Training on the CUDA engine: the compute of NeRFReplicaTrainingHandler.step (reference
+nerf/training/nerf_replica_training_handler.py:265-339) -- ray/pixel sampling, render in training
+mode (stratified jitter, sigma noise, random importance samples), MSE(coarse)+MSE(fine), backward,
+Adam, exponential learning-rate decay -- with every kernel hand-written (libnwx) and the
+data-parallel gradient all-reduce on torch.distributed (NCCL).  Dataset loading, TensorBoard, eval
+renders and checkpoint writing stay with the caller (out of scope)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import engine as _engine
+from ._lib import RenderOpts, TrainIO, check
+from .config import default_config, number
+from .engine import COARSE, FINE, STATE_KEYS, STATE_SHAPES, _f32, _ptr, _stream, linspace01
+
+PARAMS_PER_NET = 595844
+
+
+def param_offsets() -> Tuple[int, ...]:
+    buf = (C.c_int * 24)()
+    check(_lib.lib().nwx_param_offsets(buf), "nwx_param_offsets")
+    return tuple(int(v) for v in buf)
+
+
+class Trainer:
+    """Flat fp32 master parameters / gradients / Adam moments for the coarse and fine networks
+    (one [2, 595 844] tensor each, so the data-parallel all-reduce is a single NCCL call)."""
+
+    def __init__(self, eng: _engine.Engine, sd_coarse: Mapping[str, torch.Tensor], sd_fine: Mapping[str, torch.Tensor],
+                 lr: float = 5e-4, lr_decay_rate: float = 0.1, lr_decay_steps: int = 50000,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, n_samples: int = 64,
+                 n_importance: int = 128, white_bkgd: bool = False, perturb: float = 1.0, raw_noise_std: float = 1.0,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.engine, self.device, self.group = eng, eng.device, group
+        self.lr0, self.lr, self.lr_decay_rate, self.lr_decay_steps = lr, lr, lr_decay_rate, lr_decay_steps
+        self.betas, self.eps = betas, eps
+        self.n_samples, self.n_importance, self.white_bkgd = n_samples, n_importance, white_bkgd
+        self.perturb, self.raw_noise_std = perturb, raw_noise_std
+        self.offsets = param_offsets()
+        self.params = torch.empty((2, PARAMS_PER_NET), device=self.device)
+        for w, sd in ((COARSE, sd_coarse), (FINE, sd_fine)):
+            sd = _engine.normalize_state_dict(sd)
+            self.params[w].copy_(torch.cat([sd[k].detach().reshape(-1).float() for k in STATE_KEYS]).to(self.device))
+        self.grads = torch.zeros_like(self.params)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.loss = torch.zeros(2, device=self.device, dtype=torch.float64)
+        self.opt_steps = 0
+        self.pack()
+
+    # ---- parameters ------------------------------------------------------------------------
+    def state_dict(self, which: int) -> Dict[str, torch.Tensor]:
+        """Views of the flat master parameters under the reference's state_dict keys."""
+        flat = self.params[which]
+        return {k: flat[o:o + int(torch.Size(STATE_SHAPES[k]).numel())].view(STATE_SHAPES[k])
+                for k, o in zip(STATE_KEYS, self.offsets)}
+
+    def grad_dict(self, which: int) -> Dict[str, torch.Tensor]:
+        flat = self.grads[which]
+        return {k: flat[o:o + int(torch.Size(STATE_SHAPES[k]).numel())].view(STATE_SHAPES[k])
+                for k, o in zip(STATE_KEYS, self.offsets)}
+
+    def pack(self) -> None:
+        for w in (COARSE, FINE):
+            check(self.engine._lib.nwx_train_pack(self.engine._ctx, w, self.params[w].data_ptr(), _stream()),
+                  "nwx_train_pack")
+
+    def sync_inference_weights(self) -> None:
+        """Refresh the engine's inference-side copy (host constants) from the master parameters."""
+        self.engine.load_weights(COARSE, self.state_dict(COARSE))
+        self.engine.load_weights(FINE, self.state_dict(FINE))
+        self.pack()
+
+    # ---- one step ----------------------------------------------------------------------------
+    def forward_backward(self, rays: torch.Tensor, gt_rgb: torch.Tensor, t_rand: Optional[torch.Tensor] = None,
+                         u: Optional[torch.Tensor] = None, noise_coarse: Optional[torch.Tensor] = None,
+                         noise_fine: Optional[torch.Tensor] = None, want_rgb: bool = False):
+        """Render `rays` in training mode, loss = mse(rgb_c, gt) + mse(rgb_f, gt), gradients into
+        self.grads.  The three random draws of the reference (t_rand training handler:560, noise
+        model_utils.py:65, u rays.py:98) are taken on the device unless injected."""
+        rays, gt = _f32(rays, "rays"), _f32(gt_rgb, "gt_rgb")
+        N, dev = rays.shape[0], rays.device
+        Sc, Ni = self.n_samples, self.n_importance
+        if t_rand is None and self.perturb > 0.:
+            t_rand = torch.rand((N, Sc), device=dev)
+        if u is None and self.perturb > 0.:
+            u = torch.rand((N, Ni), device=dev)
+        if noise_coarse is None and self.raw_noise_std > 0.:
+            noise_coarse = torch.randn((N, Sc), device=dev) * self.raw_noise_std
+            noise_fine = torch.randn((N, Sc + Ni), device=dev) * self.raw_noise_std
+        keep = [None if t is None else _f32(t, "rand") for t in (t_rand, u, noise_coarse, noise_fine)]
+        opts = RenderOpts(Sc, Ni, int(self.white_bkgd), rays.shape[1], linspace01(Sc, dev).data_ptr(),
+                          linspace01(Ni, dev).data_ptr(), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]))
+        rgb_c = torch.empty((N, 3), device=dev) if want_rgb else None
+        rgb_f = torch.empty((N, 3), device=dev) if want_rgb else None
+        io = TrainIO(rays.data_ptr(), gt.data_ptr(), self.grads[COARSE].data_ptr(), self.grads[FINE].data_ptr(),
+                     self.loss.data_ptr(), _ptr(rgb_c), _ptr(rgb_f))
+        check(self.engine._lib.nwx_train_fwd_bwd(self.engine._ctx, C.byref(io), N, C.byref(opts), _stream()),
+              "nwx_train_fwd_bwd")
+        return (self.loss, rgb_c, rgb_f) if want_rgb else self.loss
+
+    def optimizer_step(self, global_step: int) -> None:
+        """All-reduce (mean) the gradients across ranks, Adam, re-pack, then the reference's
+        learning-rate schedule lr = lr0 * rate^(step/decay_steps) (training handler:312-315),
+        which -- as in the reference -- takes effect from the NEXT step."""
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(self.group)
+            if world > 1:
+                dist.all_reduce(self.grads, group=self.group)       # 4.77 MB, one NCCL call
+        self.opt_steps += 1
+        n = self.params.numel()
+        check(self.engine._lib.nwx_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
+                                             self.v.data_ptr(), n, self.lr, self.betas[0], self.betas[1], self.eps,
+                                             self.opt_steps, 1.0 / world, _stream()), "nwx_adam_step")
+        self.pack()
+        self.lr = self.lr0 * (self.lr_decay_rate ** (global_step / self.lr_decay_steps))
+
+    def step(self, rays: torch.Tensor, gt_rgb: torch.Tensor, global_step: int, **rand) -> torch.Tensor:
+        loss = self.forward_backward(rays, gt_rgb, **rand)
+        self.optimizer_step(global_step)
+        return loss
+
+
+class NeRFReplicaTrainingHandler:
+    """Drop-in for the compute of the reference training handler.  The reference builds its ray
+    bank and pixel bank from the Replica dataset (`initialize_rays` :243-263, `prepare_data`
+    :118-194); here they are passed in (any source, e.g. nwx.create_rays on the dataset's poses)."""
+
+    def __init__(self, office_name: str, config: Optional[Mapping], rays_train: torch.Tensor, train_rgbs: torch.Tensor,
+                 sd_coarse: Optional[Mapping] = None, sd_fine: Optional[Mapping] = None,
+                 device: Optional[torch.device] = None, seed: int = 0):
+        from .synthetic import random_state_dicts
+        cfg = default_config() if config is None else config
+        self._office_name, self._config = office_name, cfg
+        rnd, trn = cfg["rendering"], cfg["training"]
+        self._n_rays = number(rnd["n_rays"])
+        self._img_h, self._img_w = int(cfg["experiment"]["image_height"]), int(cfg["experiment"]["image_width"])
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rays_train = rays_train.to(dev).float()               # [num_images, H*W, 11]
+        self._train_rgbs = train_rgbs.to(dev).float().reshape(rays_train.shape[0], -1, 3)
+        if sd_coarse is None:
+            sd_coarse, sd_fine = random_state_dicts(seed, alpha_bias=None)
+        self._engine = _engine.Engine(dev)
+        self.trainer = Trainer(self._engine, sd_coarse, sd_fine, lr=float(trn["learning_rate"]),
+                               lr_decay_rate=float(trn["learning_rate_decay_rate"]),
+                               lr_decay_steps=int(trn["learning_rate_decay_steps"]),
+                               n_samples=int(rnd["n_samples"]), n_importance=int(rnd["n_importance"]),
+                               white_bkgd=bool(rnd["white_background"]), perturb=float(rnd["perturb"]),
+                               raw_noise_std=float(rnd["raw_noise_std"]))
+        self._gen = torch.Generator(device=dev).manual_seed(seed)
+
+    def _sample_training_data(self):
+        """One random image, n_rays random pixels with replacement (training handler:341-370)."""
+        num_img, num_ray, _ = self.rays_train.shape
+        img = int(torch.randint(0, num_img, (1,), device=self.rays_train.device, generator=self._gen))
+        pix = torch.randint(0, num_ray, (self._n_rays,), device=self.rays_train.device, generator=self._gen)
+        return self.rays_train[img, pix], self._train_rgbs[img, pix]
+
+    def step(self, global_step: int) -> Dict[str, torch.Tensor]:
+        rays, gt = self._sample_training_data()
+        loss = self.trainer.step(rays, gt, global_step)
+        mse = loss.clone()
+        psnr = -10.0 * torch.log10(mse)                            # mse2psnr, model_utils.py:8
+        return {"rgb_loss_coarse": mse[0], "rgb_loss_fine": mse[1], "total_loss": mse.sum(),
+                "psnr_coarse": psnr[0], "psnr_fine": psnr[1]}

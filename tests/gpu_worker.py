@@ -68,10 +68,48 @@ def mlp_case(variant: int, n_points: int, tap_layer: int = -1) -> dict:
     return out
 
 
+def train_case(n_rays: int) -> dict:
+    """Forward+backward of one batch against the oracle's autograd (CPU)."""
+    import nwx
+    dev = torch.device("cuda:0")
+    eng = nwx.Engine(dev)
+    diag = torch.zeros(4, dtype=torch.int32).pin_memory()
+    eng.debug_diag(diag)
+    gen = torch.Generator().manual_seed(0)
+    sd_c, sd_f = orc.init_state_dict(0, generator=gen), orc.init_state_dict(0, generator=gen)
+    tr = nwx.Trainer(eng, sd_c, sd_f)
+    g = torch.Generator().manual_seed(21)
+    fx, fy, cx, cy = orc.intrinsics(24, 32)
+    rays = orc.create_rays(1, orc.synthetic_poses(1, 3), 24, 32, fx, fy, cx, cy, 0.1, 10.0)[0]
+    rays = rays[torch.randperm(768, generator=g)[:n_rays]].contiguous()
+    gt = torch.rand(n_rays, 3, generator=g)
+    t_rand, u = torch.rand(n_rays, 64, generator=g), torch.rand(n_rays, 128, generator=g)
+    nc, nf = torch.randn(n_rays, 64, generator=g), torch.randn(n_rays, 192, generator=g)
+    out = {"n_rays": n_rays}
+    try:
+        loss = tr.forward_backward(rays.to(dev), gt.to(dev), t_rand.to(dev), u.to(dev), nc.to(dev), nf.to(dev))
+        torch.cuda.synchronize()
+    except Exception as exc:  # noqa: BLE001
+        out.update(ok=False, error=str(exc)[:300], diag=[hex(int(v) & 0xFFFFFFFF) for v in diag])
+        return out
+    lc, lf, gc, gf, _ = orc.training_loss_and_grads(rays, gt, sd_c, sd_f, orc.RenderConfig(), t_rand, u, nc, nf)
+    out.update(ok=True, loss=[float(loss[0]), float(loss[1])], loss_ref=[float(lc), float(lf)], tensors={})
+    for tag, which, ref in (("c", 0, gc), ("f", 1, gf)):
+        mine = {k: v.cpu() for k, v in tr.grad_dict(which).items()}
+        for k in orc.STATE_KEYS:
+            a, b = mine[k].double().reshape(-1), ref[k].double().reshape(-1)
+            cos = float((a @ b) / (a.norm() * b.norm() + 1e-300))
+            out["tensors"][f"{tag}.{k}"] = [round(float(a.norm() / (b.norm() + 1e-300)), 4), round(cos, 5),
+                                            bool(torch.isfinite(a).all())]
+    return out
+
+
 if __name__ == "__main__":
     kind = sys.argv[1]
     if kind == "mlp":
         res = mlp_case(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else -1)
+    elif kind == "train":
+        res = train_case(int(sys.argv[2]))
     else:
         raise SystemExit(f"unknown case {kind}")
     print("RESULT " + json.dumps(res))
