@@ -27,6 +27,18 @@ def param_offsets() -> Tuple[int, ...]:
     return tuple(int(v) for v in buf)
 
 
+def allreduce_sum_(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> float:
+    """Sum `flat` over the ranks in place (one collective for both networks' gradients) and return
+    the factor that turns the sum into the data-parallel mean (1 / world_size): per-rank batches
+    are equal, so the mean of per-rank mean-losses' gradients is the global-batch gradient."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, group=group)
+    return 1.0 / world
+
+
 class Trainer:
     """Flat fp32 master parameters / gradients / Adam moments for the coarse and fine networks
     (one [2, 595 844] tensor each, so the data-parallel all-reduce is a single NCCL call)."""
@@ -108,16 +120,12 @@ class Trainer:
         """All-reduce (mean) the gradients across ranks, Adam, re-pack, then the reference's
         learning-rate schedule lr = lr0 * rate^(step/decay_steps) (training handler:312-315),
         which -- as in the reference -- takes effect from the NEXT step."""
-        world = 1
-        if dist.is_available() and dist.is_initialized():
-            world = dist.get_world_size(self.group)
-            if world > 1:
-                dist.all_reduce(self.grads, group=self.group)       # 4.77 MB, one NCCL call
+        scale = allreduce_sum_(self.grads, self.group)               # 4.77 MB, one NCCL call
         self.opt_steps += 1
         n = self.params.numel()
         check(self.engine._lib.nwx_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
                                              self.v.data_ptr(), n, self.lr, self.betas[0], self.betas[1], self.eps,
-                                             self.opt_steps, 1.0 / world, _stream()), "nwx_adam_step")
+                                             self.opt_steps, scale, _stream()), "nwx_adam_step")
         self.pack()
         self.lr = self.lr0 * (self.lr_decay_rate ** (global_step / self.lr_decay_steps))
 

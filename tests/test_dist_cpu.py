@@ -52,6 +52,27 @@ def test_sharded_render_gathers_full_frame_gloo_world2():
         assert dict(results) == {0: True, 1: True}
 
 
+def _grad_worker(rank: int, world: int, port: int, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nwx.training import allreduce_sum_
+    flat = torch.full((2, 1000), float(rank + 1))
+    scale = allreduce_sum_(flat)
+    results[rank] = bool(scale == 0.5 and torch.equal(flat * scale, torch.full((2, 1000), 1.5)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_mean_gloo_world2():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, results), nprocs=world, join=True)
+        assert dict(results) == {0: True, 1: True}
+    from nwx.training import allreduce_sum_
+    t = torch.ones(4)
+    assert allreduce_sum_(t) == 1.0 and torch.equal(t, torch.ones(4))      # no process group: identity
+
+
 def test_single_process_is_identity():
     from nwx.dist import render_sharded
     assert torch.equal(render_sharded(1000, _fake_render), _fake_render(0, 1000))

@@ -61,6 +61,13 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
+    # data-parallel invariant: every rank holds bit-identical parameters after the same steps
+    chk = tr.params.double().sum().reshape(1)
+    same = True
+    if world > 1:
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        same = all(bool(torch.equal(c, allc[0])) for c in allc)
     if rank == 0:
         pts = args.rays * 256
         print(json.dumps({
@@ -68,7 +75,7 @@ def main():
             "n_gpus": world, "ms_per_step": ms_step, "rays_per_s": world * args.rays / (ms_step * 1e-3),
             "tflops_per_gpu": FLOP_PER_POINT_TRAIN * pts / (ms_step * 1e-3) / 1e12,
             "kernel_launches_per_step": (nwx.engine.launch_count() - launches0) / args.steps,
-            "loss": [float(loss[0]), float(loss[1])]}))
+            "loss": [float(loss[0]), float(loss[1])], "params_identical_across_ranks": same}))
     if world > 1:
         dist.destroy_process_group()
 
