@@ -40,11 +40,31 @@ __device__ __forceinline__ int layer_gkb0(int l) {     // global K-block index o
   return l == 0 ? 0 : (l <= 5 ? 1 + 4 * (l - 1) : 22 + 4 * (l - 6));
 }
 
+// sin / cos of 2^k * x for k = 0..9 without ten full-range sincosf calls.  With t = x / (2 pi) held as
+// an unevaluated float pair (hi + lo), 2^k * t_hi is exact (power-of-two scaling), its fractional part
+// f is exact, and adding 2^k * t_lo leaves the phase accurate to ~1e-7 turns even at k = 9; the
+// reduced angle 2 pi f in [-pi, pi] then goes to MUFU.SIN/COS (abs error 2^-21.4, a tenth of a bf16
+// half-ulp at |v| >= 2^-4).  ~7 instructions per sin/cos pair instead of ~40.
+__device__ __forceinline__ void sincos_pow2(float t_hi, float t_lo, float scale, float& s, float& c) {
+  const float a = t_hi * scale;                                   // exact
+  const float f = (a - rintf(a)) + t_lo * scale;                  // fractional turns, |f| <= 0.5 + eps
+  const float r = f * 6.283185307179586f;
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
 // 63 positional-encoding features of one point (+1 zero pad) as 32 packed bf16 pairs.
 // Column order of Embedding.embed (embedding.py:31-38,48): x/s, then per k: sin(x/s*2^k)(3), cos(..)(3).
 __device__ __forceinline__ void encode_point(float px, float py, float pz, uint32_t (&pk)[32]) {
   float f[64];
   const float x[3] = {__fdiv_rn(px, 10.0f), __fdiv_rn(py, 10.0f), __fdiv_rn(pz, 10.0f)};   // scalar_factor 10
+  float t_hi[3], t_lo[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {                                   // t = x / (2 pi) as hi + lo
+    constexpr float kInv2PiHi = 0.15915494309189535f, kInv2PiLo = 6.4206382e-09f;   // 1/(2 pi) = hi + lo in fp32
+    t_hi[a] = x[a] * kInv2PiHi;
+    t_lo[a] = fmaf(x[a], kInv2PiHi, -t_hi[a]) + x[a] * kInv2PiLo;
+  }
   f[0] = x[0]; f[1] = x[1]; f[2] = x[2];
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
@@ -52,7 +72,7 @@ __device__ __forceinline__ void encode_point(float px, float py, float pz, uint3
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       float s, c;
-      sincosf(x[a] * sc, &s, &c);
+      sincos_pow2(t_hi[a], t_lo[a], sc, s, c);
       f[3 + 6 * k + a] = s;
       f[3 + 6 * k + 3 + a] = c;
     }
@@ -79,44 +99,61 @@ enum { kEpiRelu = 0, kEpiReluSigma = 1, kEpiLinear = 2 };
 // Hidden-layer epilogue of one thread (= one point / TMEM lane) over its 128-column half:
 // accumulator -> +bias -> (ReLU) -> bf16 -> the next layer's swizzled A-operand tile.
 // Returns this half's partial of the fp32 sigma head when kMode == kEpiReluSigma.
+// One 32-column chunk of the hidden-layer epilogue: +bias -> (ReLU) -> bf16 -> swizzled A tile.
+template <int kMode, bool kTap, bool kSave>
+__device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, const uint32_t (&v)[32], int col, uint32_t hrow,
+                                               int row, float* tap_row, uint8_t* grow, float& sig) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float a = __uint_as_float(v[j]) + cst.bias[l][col + j];
+    const float b = __uint_as_float(v[j + 1]) + cst.bias[l][col + j + 1];
+    if (kMode == kEpiReluSigma) {                  // sigma head on fp32 relu(h7), nerf_model.py:63
+      sig = fmaf(fmaxf(a, 0.f), cst.w_alpha[col + j], sig);
+      sig = fmaf(fmaxf(b, 0.f), cst.w_alpha[col + j + 1], sig);
+    }
+    if (kTap && tap_row) {
+      tap_row[col + j] = kMode == kEpiLinear ? a : fmaxf(a, 0.f);
+      tap_row[col + j + 1] = kMode == kEpiLinear ? b : fmaxf(b, 0.f);
+    }
+    pk[j >> 1] = (kMode == kEpiLinear) ? pack_bf16x2(a, b) : pack_bf16x2_relu(a, b);   // feature: no ReLU (:64)
+  }
+  const uint32_t kbase = hrow + (col >> 6) * kABlock;
+  const int j0 = (col & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  if (kSave) {                                   // training: keep the same tile image in HBM for the backward
+    uint8_t* gk = grow + (size_t)(col >> 6) * kTileImgBytes;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(gk + (((j0 + q) ^ (row & 7)) << 4)) =
+          make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
+// Hidden-layer epilogue of one thread (= one point / TMEM lane) over its 128-column half, software
+// pipelined two deep: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed (the
+// epilogue is latency-bound: 2 epilogue warps per scheduler), and the bias loads are free to move
+// above the TMEM wait.  Returns this half's partial of the fp32 sigma head (kEpiReluSigma).
 template <int kMode, bool kTap, bool kSave>
 __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, uint32_t d_tmem, uint32_t hrow,
                                                  int row, int wg, float* tap_row, uint8_t* grow) {
   float sig = 0.f;
-#pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
-    const int col = wg * 128 + cc * 32;
-    uint32_t v[32];
-    tmem_ld32(d_tmem + col, v);
-    tmem_wait_ld();
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const float a = __uint_as_float(v[j]) + cst.bias[l][col + j];
-      const float b = __uint_as_float(v[j + 1]) + cst.bias[l][col + j + 1];
-      if (kMode == kEpiReluSigma) {                  // sigma head on fp32 relu(h7), nerf_model.py:63
-        sig = fmaf(fmaxf(a, 0.f), cst.w_alpha[col + j], sig);
-        sig = fmaf(fmaxf(b, 0.f), cst.w_alpha[col + j + 1], sig);
-      }
-      if (kTap && tap_row) {
-        tap_row[col + j] = kMode == kEpiLinear ? a : fmaxf(a, 0.f);
-        tap_row[col + j + 1] = kMode == kEpiLinear ? b : fmaxf(b, 0.f);
-      }
-      pk[j >> 1] = (kMode == kEpiLinear) ? pack_bf16x2(a, b) : pack_bf16x2_relu(a, b);   // feature: no ReLU (:64)
-    }
-    const uint32_t kbase = hrow + (col >> 6) * kABlock;
-    const int j0 = (col & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    if (kSave) {                                   // training: keep the same tile image in HBM for the backward
-      uint8_t* gk = grow + (size_t)(col >> 6) * kTileImgBytes;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(gk + (((j0 + q) ^ (row & 7)) << 4)) =
-            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    }
-  }
+  const int col0 = wg * 128;
+  uint32_t va[32], vb[32];
+  tmem_ld32(d_tmem + col0, va);
+  tmem_wait_ld_dep(va);
+  tmem_ld32(d_tmem + col0 + 32, vb);
+  epilogue_chunk<kMode, kTap, kSave>(cst, l, va, col0, hrow, row, tap_row, grow, sig);
+  tmem_wait_ld_dep(vb);
+  tmem_ld32(d_tmem + col0 + 64, va);
+  epilogue_chunk<kMode, kTap, kSave>(cst, l, vb, col0 + 32, hrow, row, tap_row, grow, sig);
+  tmem_wait_ld_dep(va);
+  tmem_ld32(d_tmem + col0 + 96, vb);
+  epilogue_chunk<kMode, kTap, kSave>(cst, l, va, col0 + 64, hrow, row, tap_row, grow, sig);
+  tmem_wait_ld_dep(vb);
+  epilogue_chunk<kMode, kTap, kSave>(cst, l, vb, col0 + 96, hrow, row, tap_row, grow, sig);
   return sig;
 }
 

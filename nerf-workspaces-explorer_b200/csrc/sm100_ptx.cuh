@@ -53,8 +53,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      // default .acquire.cta: a .cluster scope adds a CCTL.IVALL (L1 invalidate) to every probe
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      // default .acquire.cta: a .cluster scope adds a CCTL.IVALL (L1 invalidate) to every probe.
+      // The suspend-time hint lets the hardware park the warp (it is woken by the arrival), so a
+      // waiting warp executes a handful of probes instead of spinning.
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
@@ -148,6 +150,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, expressed as a data dependency on the loaded registers instead of a memory clobber:
+// the values cannot be consumed before the wait, while unrelated loads (biases from the constant
+// bank, masks from global) stay free to be scheduled above it.
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
 
 // {lo, hi} fp32 -> packed bf16x2 (lo in the low half = lower address), optional fused ReLU.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
