@@ -133,6 +133,25 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------- GPU arm ----
+def mlp_dram_traffic_per_step():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the two mlp_fused_kernel launches of one step,
+    from the committed `ncu --set full` capture (profiles/r01_ncu_mlp_full.csv); None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_ncu_mlp_full.csv")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rows = list(csv.reader(f))
+    hdr, units = rows[0], rows[1]
+    total = 0.0
+    for r in rows[2:]:
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            total += float(r[i]) * scale
+    return total
+
+
 def measured_peak_tflops():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -246,7 +265,10 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "mlp_fused_kernel (2 launches/step)",
+                         "frac": achieved / peak, "traffic": mlp_dram_traffic_per_step(),
+                         "traffic_note": "DRAM bytes of the step's two launches, ncu --set full (profiles/r01_ncu_mlp_full.csv); "
+                                         "algorithmic: 20 B/point + 556 B/ray = 1.74 GB",
+                         "kernel": "mlp_fused_kernel (2 launches/step)",
                          "peak_source": peak_src, "flop_per_step": mlp_flop, "kernel_ms_per_step": mlp_ms},
             "stages_ms": {k: mean(k) for k in E.Engine.STAGES},
         }

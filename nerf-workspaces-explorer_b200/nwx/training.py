@@ -88,6 +88,49 @@ class Trainer:
         self.engine.load_weights(FINE, self.state_dict(FINE))
         self.pack()
 
+    # ---- checkpoints (reference format, training handler:394-409) ---------------------------------
+    def checkpoint(self, global_step: int) -> Dict[str, object]:
+        """{global_step, network_coarse_state_dict, network_fine_state_dict, optimizer_state_dict}; the
+        optimizer entry has torch.optim.Adam's layout for the 48 parameters (coarse then fine, the
+        order of `learnable_params`, training handler:227-234), so the reference can resume from it."""
+        sds = [{k: v.detach().clone().cpu() for k, v in self.state_dict(w).items()} for w in (COARSE, FINE)]
+        state, idx = {}, 0
+        for w in (COARSE, FINE):
+            for k, o in zip(STATE_KEYS, self.offsets):
+                n = int(torch.Size(STATE_SHAPES[k]).numel())
+                state[idx] = {"step": torch.tensor(float(self.opt_steps)),
+                              "exp_avg": self.m[w, o:o + n].view(STATE_SHAPES[k]).clone().cpu(),
+                              "exp_avg_sq": self.v[w, o:o + n].view(STATE_SHAPES[k]).clone().cpu()}
+                idx += 1
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(idx))}
+        return {"global_step": global_step, "network_coarse_state_dict": sds[0], "network_fine_state_dict": sds[1],
+                "optimizer_state_dict": {"state": state, "param_groups": [group]}}
+
+    def save_checkpoint(self, path: str, global_step: int) -> None:
+        torch.save(self.checkpoint(global_step), path)
+
+    def load_checkpoint(self, ckpt: Mapping[str, object]) -> int:
+        """Resume from a checkpoint dict in the reference format (either key style)."""
+        for w, name in ((COARSE, "network_coarse_state_dict"), (FINE, "network_fine_state_dict")):
+            sd = _engine.normalize_state_dict(ckpt[name])
+            self.params[w].copy_(torch.cat([sd[k].detach().reshape(-1).float() for k in STATE_KEYS]).to(self.device))
+        opt = ckpt.get("optimizer_state_dict")
+        if opt and opt.get("state"):
+            idx = 0
+            for w in (COARSE, FINE):
+                for k, o in zip(STATE_KEYS, self.offsets):
+                    n = int(torch.Size(STATE_SHAPES[k]).numel())
+                    st = opt["state"][idx]
+                    self.m[w, o:o + n].copy_(st["exp_avg"].reshape(-1).to(self.device))
+                    self.v[w, o:o + n].copy_(st["exp_avg_sq"].reshape(-1).to(self.device))
+                    self.opt_steps = int(st["step"])
+                    idx += 1
+            self.lr = float(opt["param_groups"][0]["lr"])
+        self.pack()
+        return int(ckpt.get("global_step", 0))
+
     # ---- one step ----------------------------------------------------------------------------
     def forward_backward(self, rays: torch.Tensor, gt_rgb: torch.Tensor, t_rand: Optional[torch.Tensor] = None,
                          u: Optional[torch.Tensor] = None, noise_coarse: Optional[torch.Tensor] = None,

@@ -137,3 +137,36 @@ def test_training_handler_step():
     out = h.step(0)
     assert set(out) == {"rgb_loss_coarse", "rgb_loss_fine", "total_loss", "psnr_coarse", "psnr_fine"}
     assert torch.isfinite(out["total_loss"]) and float(out["total_loss"]) > 0
+
+
+def test_checkpoint_round_trip_reference_format(tmp_path):
+    """Trainer -> reference-format .ckpt -> (a) torch.optim.Adam accepts the optimizer state,
+    (b) the inference handler loads it through initialize_models (handler:130-141) and renders with
+    exactly the trained weights, (c) a second Trainer resumes on the same trajectory (the head gradients
+    are accumulated with fp32 atomics, so two runs agree to rounding, not bitwise)."""
+    import nwx
+    eng = nwx.Engine(torch.device(DEV))
+    tr = nwx.Trainer(eng, *_nets(), perturb=0.0, raw_noise_std=0.0)
+    fx, fy, cx, cy = orc.intrinsics(24, 32)
+    rays = orc.create_rays(1, orc.synthetic_poses(1, 3), 24, 32, fx, fy, cx, cy, 0.1, 10.0)[0][:128].to(DEV)
+    gt = torch.full((128, 3), 0.5, device=DEV)
+    for step in range(2):
+        tr.step(rays, gt, step)
+    path = str(tmp_path / "000002.ckpt")
+    tr.save_checkpoint(path, 2)
+    ckpt = torch.load(path)
+    assert set(ckpt) == {"global_step", "network_coarse_state_dict", "network_fine_state_dict", "optimizer_state_dict"}
+    params = [torch.nn.Parameter(v.clone()) for sd in (ckpt["network_coarse_state_dict"], ckpt["network_fine_state_dict"])
+              for v in sd.values()]
+    torch.optim.Adam(params, lr=5e-4).load_state_dict(ckpt["optimizer_state_dict"])      # the reference's optimizer
+    h = nwx.NeRFReplicaInferenceHandler("office_tokyo", path)
+    h.initialize_models()
+    tr.sync_inference_weights()
+    a = h._volumetric_rendering(rays)["rgb_fine"]
+    b = eng.render_rays(rays, want=("rgb_fine",))["rgb_fine"]
+    assert torch.equal(a, b)
+    tr2 = nwx.Trainer(nwx.Engine(torch.device(DEV)), *_nets(), perturb=0.0, raw_noise_std=0.0)
+    assert tr2.load_checkpoint(ckpt) == 2
+    tr.step(rays, gt, 2); tr2.step(rays, gt, 2)
+    assert torch.equal(tr.m != 0, tr2.m != 0)
+    assert float((tr.params - tr2.params).abs().max()) <= 1e-6
