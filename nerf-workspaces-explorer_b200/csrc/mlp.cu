@@ -104,6 +104,7 @@ template <int kMode, bool kTap, bool kSave>
 __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, const uint32_t (&v)[32], int col, uint32_t hrow,
                                                int row, float* tap_row, uint8_t* grow, float& sig) {
   uint32_t pk[16];
+  const bool no_sts = kTap && hrow == 0;          // timing experiment (debug instantiation only)
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     const float a = __uint_as_float(v[j]) + cst.bias[l][col + j];
@@ -120,9 +121,13 @@ __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, cons
   }
   const uint32_t kbase = hrow + (col >> 6) * kABlock;
   const int j0 = (col & 63) >> 3;
+  if (!no_sts) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  } else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) {
+    st_shared_v4(kbase, pk[0], pk[5], pk[10], pk[15]);      // keeps the math alive
+  }
   if (kSave) {                                   // training: keep the same tile image in HBM for the backward
     uint8_t* gk = grow + (size_t)(col >> 6) * kTileImgBytes;
 #pragma unroll
@@ -162,6 +167,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst_param) {
   using L = SmemLayout<kPair, kStages>;
   const MlpConsts& cst = kTrain ? c_fwd_train_consts[args.which] : cst_param;
+  // Timeline trace (debug instantiation only, nwx_debug_tap(ctx, -2, buf)): CTA 0 records
+  // (tag, clock) pairs per role into buf[role][event][2] so the critical path can be read off.
+  constexpr int kTraceEvents = 4096;
+  const bool tracing = kTap && args.dbg_out != nullptr && args.dbg_layer == -2 && blockIdx.x == 0;
+  uint32_t trace_n = 0;
+  auto trace = [&](int role, int ev, int it, int l, int t) {
+    if (kTap && tracing && trace_n < kTraceEvents) {
+      uint32_t* rec = reinterpret_cast<uint32_t*>(args.dbg_out) + ((size_t)role * kTraceEvents + trace_n) * 2;
+      rec[0] = (uint32_t)(ev * 100000 + it * 1000 + l * 10 + t);
+      rec[1] = (uint32_t)clock64();
+      ++trace_n;
+    }
+  };
   constexpr int kCG = kPair ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -213,7 +231,9 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           for (int t = 0; t < (kResident ? 1 : 2); ++t) {
             for (int kb = 0; kb < chunk_nkb(c); ++kb, ++fill) {
               const uint32_t stage = fill % kStages, round = fill / kStages;
+              trace(0, 31, it, l, kb);
               mbar_wait(sbase + L::w_empty + 8 * stage, (round & 1) ^ 1, wc);
+              trace(0, 32, it, l, kb);
               const uint32_t bar = sbase + L::w_full + 8 * stage;
               mbar_arrive_expect_tx(bar, bytes);
               const uint8_t* src = args.wimg + kblock_offset(layer_gkb0(l) + chunk_kb0(c) + kb) + rank * bytes;
@@ -236,12 +256,14 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             const bool first_chunk = (c != 6), last_chunk = (c != 5);
             const uint32_t idesc = umma_idesc_bf16(kTileM * kCG, l == 9 ? kViewHidden : kHidden);
             for (int t = 0; t < 2; ++t) {
+              trace(1, 1, it, l, t);
               if (first_chunk) {
                 if (l == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
                 // a_ready[t] completes once per layer epilogue: phase index = 10*it + l - 1
                 if (l != 0 || it != 0) mbar_wait(sbase + L::a_ready + 8 * t, (l + 1) & 1, wc);
                 tc_fence_after();
               }
+              trace(1, 2, it, l, t);
               const uint32_t d_tmem = tmem_base + t * kHidden;
               for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t f = kResident ? fill + kb : fill++;
@@ -264,6 +286,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
               }
               if (last_chunk) umma_commit<kCG>(sbase + L::acc_full + 8 * t);
               if (c == 5) umma_commit<kCG>(sbase + L::pe_free + 8 * t);
+              trace(1, 3, it, l, t);
             }
             if (kResident) fill += nkb;
           }
@@ -292,7 +315,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
         } else if (args.pts) {
           px = __ldg(args.pts + p * 3 + 0); py = __ldg(args.pts + p * 3 + 1); pz = __ldg(args.pts + p * 3 + 2);
         } else {
-          const int64_t ray = p / args.S;
+          const int64_t ray = (p >> 32) == 0 ? (int64_t)((uint32_t)p / (uint32_t)args.S) : p / args.S;   // 32-bit divide when it fits
           const float* r = args.rays + ray * args.ray_dim;
           const float zz = __ldg(args.z + p);
           px = __fadd_rn(__ldg(r + 0), __fmul_rn(__ldg(r + 3), zz));   // inference handler:223
@@ -308,7 +331,9 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
         } else {
           encode_point(px, py, pz, pk);
         }
+        if (row == 0) trace(2, 21, it, 0, t);
         if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
+        if (row == 0) trace(2, 22, it, 0, t);
         const uint32_t dst = sbase + L::pe0 + t * kABlock + row * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -339,14 +364,19 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     for (int it = 0; it < iters; ++it) {
       for (int l = 0; l < kNumLayers; ++l) {
         for (int t = 0; t < 2; ++t) {
+          if (lane == 0 && quad == 0) trace(3 + wg, 11, it, l, t);
           mbar_wait(sbase + L::acc_full + 8 * t, l & 1, wc);   // phase index = 10*it + l
           tc_fence_after();
+          if (lane == 0 && quad == 0) trace(3 + wg, 12, it, l, t);
           const uint32_t d_tmem = lane_addr + t * kHidden;
           const int64_t p = tile_of(it, t) * kTileM + row;
           float* tap_row = nullptr;
           if (kTap && args.dbg_out != nullptr && args.dbg_layer == l && p < P) tap_row = args.dbg_out + p * kHidden;
-          if (l < 9) {
-            const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
+          if (kTap && args.dbg_layer == -4 && args.dbg_out != nullptr) {
+            // timing experiment: no epilogue work at all, only the barrier handshake
+          } else if (l < 9) {
+            const uint32_t hrow = (kTap && args.dbg_layer == -3 && args.dbg_out != nullptr)
+                                      ? 0u : sbase + L::h0 + t * kHBytes + row * 128;
             const bool save = kTrain && args.acts != nullptr && tile_of(it, t) < args.n_tiles;
             uint8_t* grow = save ? args.acts + tile_img_offset(act_slot_kb0(l + 1), 4, args.n_tiles, tile_of(it, t), 0) + row * 128
                                  : nullptr;
@@ -365,7 +395,8 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           } else {
             // views layer (N = 128): + (b_view + W_view[:,256:] . pe(dir)), ReLU, fp32 rgb head
             const int64_t pc = p < P ? p : P - 1;
-            const float* db = args.dirbias + (pc / args.S) * kViewHidden;
+            const int64_t dray = (pc >> 32) == 0 ? (int64_t)((uint32_t)pc / (uint32_t)args.S) : pc / args.S;
+            const float* db = args.dirbias + dray * kViewHidden;
             float r = 0.f, g = 0.f, b = 0.f;
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
@@ -410,6 +441,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (lane == 0) {
             if (kPair) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
             else mbar_arrive(sbase + L::a_ready + 8 * t);
+            if (quad == 0) trace(3 + wg, 13, it, l, t);
           }
         }
       }

@@ -545,6 +545,7 @@ head_grads_kernel(const HeadArgs a) {
     if (tid < kViewHidden) {
       float gsum = 0.f;
       int64_t ray = p0 / a.S;
+      int left = a.S - (int)(p0 - ray * a.S);                   // points left in the current ray (no per-point division)
       for (int r0 = 0; r0 < n; r0 += 8) {
         float4 d[8];
         float h[8];
@@ -557,12 +558,12 @@ head_grads_kernel(const HeadArgs a) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (r0 + q >= n) break;
-          const int64_t pr = (p0 + r0 + q) / a.S;
-          if (pr != ray) {                                      // ray boundary: fold the ray's sum of g_v
+          if (left == 0) {                                      // ray boundary: fold the ray's sum of g_v
 #pragma unroll
             for (int i = 0; i < kPeDir; ++i) d_dir[i] = fmaf(gsum, __ldg(a.pe_dir + ray * kPeDir + i), d_dir[i]);
-            gsum = 0.f; ray = pr;
+            gsum = 0.f; ++ray; left = a.S;
           }
+          --left;
           d_wr[0] = fmaf(d[q].x, h[q], d_wr[0]); d_wr[1] = fmaf(d[q].y, h[q], d_wr[1]); d_wr[2] = fmaf(d[q].z, h[q], d_wr[2]);
           if (h[q] > 0.f) gsum += fmaf(wr[0], d[q].x, fmaf(wr[1], d[q].y, wr[2] * d[q].z));
           if (tid == 0) { d_b[0] += d[q].x; d_b[1] += d[q].y; d_b[2] += d[q].z; d_b[3] += d[q].w; }

@@ -27,4 +27,20 @@ for v in [int(a) for a in sys.argv[1:]] or [1, 2, 3]:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     res[v] = {"ms": ms, "tflops": 1186816 * H * W * 192 / ms / 1e9}
+# timing experiments in the debug instantiation (results are wrong on purpose)
+eng.set_mlp_variant(1)
+dummy = torch.zeros(5 * 4096 * 2, device=dev)
+for mode, name in ((-5, "debug instantiation, normal"), (-3, "no STS in hidden epilogues"), (-4, "no epilogue work")):
+    eng.debug_tap(mode, dummy)
+    for _ in range(2):
+        eng.mlp_forward(E.FINE, rays, z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        eng.mlp_forward(E.FINE, rays, z)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    res[name] = {"ms": ms, "tflops": 1186816 * H * W * 192 / ms / 1e9}
+eng.debug_tap(-1, None)
 print(json.dumps(res))
