@@ -93,7 +93,7 @@ __device__ __forceinline__ float ray_dnorm(const float* __restrict__ rays_d, int
 }
 
 template <int K>
-__global__ void __launch_bounds__(kCompWarps * 32)
+__global__ void __launch_bounds__(kCompWarps * 32, 4)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
                      int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
@@ -104,23 +104,46 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
   int bad = 0;
   for (int64_t ray = warp0; ray < N; ray += nwarps) {
-    RaySample sm[K];
-    load_ray<K>(raw, z, noise, ray, S, lane, ray_dnorm(rays_d, d_stride, ray), sm);
+    // every load of the ray is issued before any math (K float4 + K (+K) scalar loads in flight per
+    // lane); the chunks are then consumed in order, nothing per-sample is kept: 64 registers,
+    // 4 blocks of 8 warps per SM.
+    float zr[K], nz[K];
+    float4 rw[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int s = j * 32 + lane;
+      const int64_t idx = ray * S + (s < S ? s : S - 1);
+      zr[j] = ldg_stream(z + idx);
+      rw[j] = ldg_stream4(reinterpret_cast<const float4*>(raw) + idx);
+      nz[j] = noise ? ldg_stream(noise + idx) : 0.0f;
+    }
+    const float dnorm = ray_dnorm(rays_d, d_stride, ray);
     double carry = 1.0;
     float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      const double incl = warp_incl_prod((double)sm[j].t, lane);
+      const int s = j * 32 + lane;
+      float znext = __shfl_down_sync(kFull, zr[j], 1);
+      const float zhead = __shfl_sync(kFull, zr[(j + 1 < K) ? j + 1 : j], 0);
+      if (lane == 31) znext = zhead;
+      float dist = (s >= S - 1) ? 1e10f : __fsub_rn(znext, zr[j]);          // :51,:56
+      dist = __fmul_rn(dist, dnorm);                                        // :60
+      const float sg = noise ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
+      float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg, 0.0f), dist)));   // :49
+      float t = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);                   // :75
+      if (s >= S) { alpha = 0.0f; t = 1.0f; }                               // padding lanes: neutral
+      const double incl = warp_incl_prod((double)t, lane);
       double excl = __shfl_up_sync(kFull, incl, 1);
       if (lane == 0) excl = 1.0;
-      const float T = (float)(carry * excl);                              // :75 (cumprod, exclusive)
+      const float T = (float)(carry * excl);                                // :75 (cumprod, exclusive)
       carry *= __shfl_sync(kFull, incl, 31);
-      const float w = __fmul_rn(sm[j].alpha, T);
-      const int s = j * 32 + lane;
+      const float w = __fmul_rn(alpha, T);
       if (s < S) {
         if (weights) weights[ray * S + s] = w;
-        a_r += __fmul_rn(w, sm[j].c[0]); a_g += __fmul_rn(w, sm[j].c[1]); a_b += __fmul_rn(w, sm[j].c[2]);
-        a_d += __fmul_rn(w, sm[j].z);
+        a_r += __fmul_rn(w, sigmoidf_rn(rw[j].x));                          // :62,:84
+        a_g += __fmul_rn(w, sigmoidf_rn(rw[j].y));
+        a_b += __fmul_rn(w, sigmoidf_rn(rw[j].z));
+        a_d += __fmul_rn(w, zr[j]);
         a_w += w;
       }
     }
@@ -139,9 +162,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       if (depth) depth[ray] = a_d;
       const float chk[6] = {a_r, a_g, a_b, dspv, a_w, a_d};
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        if (chk[q] != chk[q]) bad |= 1;
-        else if (fabsf(chk[q]) == INFINITY) bad |= 2;
+      for (int c = 0; c < 6; ++c) {
+        if (chk[c] != chk[c]) bad |= 1;
+        else if (fabsf(chk[c]) == INFINITY) bad |= 2;
       }
     }
   }
@@ -204,7 +227,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 
 static inline unsigned comp_grid(int64_t N) {
   int64_t blocks = (N + kCompWarps - 1) / kCompWarps;
-  const int64_t cap = (int64_t)num_sms() * 8;     // 8 blocks x 8 warps = 64 resident warps per SM
+  const int64_t cap = (int64_t)num_sms() * 8;     // up to 8 blocks x 8 warps resident per SM
   return (unsigned)(blocks < cap ? blocks : cap);
 }
 
