@@ -250,8 +250,9 @@ extern "C" int nwx_composite_fwd(const float* raw, const float* z, const float* 
                                  const float* noise, int64_t N, int S, int white_bkgd, float* rgb,
                                  float* disp, float* acc, float* depth, float* weights, int32_t* flags,
                                  void* stream) {
-  NWX_REQUIRE(raw && z && rays_d && rgb && d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
+  NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
   if (N == 0) return NWX_OK;
+  NWX_REQUIRE(raw && z && rays_d && rgb);
   auto st = (cudaStream_t)stream;
   NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
                         raw, z, rays_d, d_stride, noise, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags)));
@@ -263,8 +264,9 @@ extern "C" int nwx_composite_bwd(const float* raw, const float* z, const float* 
                                  const float* noise, const float* weights, const float* d_rgb, int64_t N,
                                  int S, int white_bkgd, float* d_raw, void* stream) {
   (void)weights;   // recomputed from raw: cheaper than re-reading 4 B/sample and exact for alpha = 0
-  NWX_REQUIRE(raw && z && rays_d && d_rgb && d_raw && d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
+  NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
   if (N == 0) return NWX_OK;
+  NWX_REQUIRE(raw && z && rays_d && d_rgb && d_raw);
   auto st = (cudaStream_t)stream;
   NWX_DISPATCH_K(S, (nwx::composite_bwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
                         raw, z, rays_d, d_stride, noise, d_rgb, N, S, white_bkgd, d_raw)));

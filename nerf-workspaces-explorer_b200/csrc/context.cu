@@ -186,8 +186,9 @@ static int run_mlp(nwx_ctx* ctx, int which, const float* rays, int ray_dim, cons
 
 extern "C" int nwx_mlp_forward(nwx_ctx* ctx, int which, const float* rays, int ray_dim, const float* z,
                                int64_t N, int S, float* raw_out, void* stream) {
-  NWX_REQUIRE(ctx && rays && z && raw_out && (which == 0 || which == 1) && ray_dim >= NWX_RAY_DIM && S >= 1 && N >= 0);
+  NWX_REQUIRE(ctx && (which == 0 || which == 1) && ray_dim >= NWX_RAY_DIM && S >= 1 && N >= 0);
   if (N == 0) return NWX_OK;
+  NWX_REQUIRE(rays && z && raw_out);
   int rc = ensure_scratch(ctx, (size_t)N * nwx::kViewHidden);
   if (rc) return rc;
   return run_mlp(ctx, which, rays, ray_dim, z, nullptr, rays + 8, ray_dim, N, N * S, S, ctx->scratch, raw_out,
@@ -196,8 +197,9 @@ extern "C" int nwx_mlp_forward(nwx_ctx* ctx, int which, const float* rays, int r
 
 extern "C" int nwx_mlp_forward_points(nwx_ctx* ctx, int which, const float* pts, const float* dirs, int64_t P,
                                       int pts_per_dir, float* raw_out, void* stream) {
-  NWX_REQUIRE(ctx && pts && dirs && raw_out && (which == 0 || which == 1) && P >= 0 && pts_per_dir >= 1);
+  NWX_REQUIRE(ctx && (which == 0 || which == 1) && P >= 0 && pts_per_dir >= 1);
   if (P == 0) return NWX_OK;
+  NWX_REQUIRE(pts && dirs && raw_out);
   const int64_t n_dir = (P + pts_per_dir - 1) / pts_per_dir;
   int rc = ensure_scratch(ctx, (size_t)n_dir * nwx::kViewHidden);
   if (rc) return rc;
@@ -207,8 +209,9 @@ extern "C" int nwx_mlp_forward_points(nwx_ctx* ctx, int which, const float* pts,
 
 extern "C" int nwx_mlp_forward_embedded(nwx_ctx* ctx, int which, const float* x, int64_t P, float* raw_out,
                                         void* stream) {
-  NWX_REQUIRE(ctx && x && raw_out && (which == 0 || which == 1) && P >= 0);
+  NWX_REQUIRE(ctx && (which == 0 || which == 1) && P >= 0);
   if (P == 0) return NWX_OK;
+  NWX_REQUIRE(x && raw_out);
   int rc = ensure_scratch(ctx, (size_t)P * nwx::kViewHidden);
   if (rc) return rc;
   return run_mlp(ctx, which, nullptr, 0, nullptr, nullptr, x + nwx::kPeXyz, nwx::kPeXyz + nwx::kPeDir, P, P, 1,
@@ -217,7 +220,9 @@ extern "C" int nwx_mlp_forward_embedded(nwx_ctx* ctx, int which, const float* x,
 
 extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const nwx_render_opts* o,
                                const nwx_render_out* out, void* stream) {
-  NWX_REQUIRE(ctx && rays && o && out && out->rgb_fine && N >= 0);
+  NWX_REQUIRE(ctx && o && out && N >= 0);
+  if (N == 0) return NWX_OK;
+  NWX_REQUIRE(rays && out->rgb_fine);
   NWX_REQUIRE(o->n_samples >= 11 && o->n_samples <= 128 && o->n_importance >= 1 && o->n_importance <= 128);
   NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin));
   if (N == 0) return NWX_OK;

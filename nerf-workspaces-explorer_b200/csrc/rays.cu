@@ -123,7 +123,9 @@ int launch_embed(const float* x, int x_stride, int64_t P, int num_freqs, float s
 }  // namespace nwx
 
 extern "C" int nwx_embed(const float* x, int64_t P, int num_freqs, float scalar_factor, float* out, void* stream) {
-  NWX_REQUIRE(x && out && P >= 0 && num_freqs >= 0 && num_freqs <= 16 && scalar_factor != 0.0f);
+  NWX_REQUIRE(P >= 0 && num_freqs >= 0 && num_freqs <= 16 && scalar_factor != 0.0f);
+  if (P == 0) return NWX_OK;
+  NWX_REQUIRE(x && out);
   return nwx::launch_embed(x, 3, P, num_freqs, scalar_factor, out, (cudaStream_t)stream);
 }
 
@@ -147,8 +149,9 @@ extern "C" int nwx_raygen(const float* c2w, int B, int H, int W, float fx, float
 
 extern "C" int nwx_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals,
                             const float* t_rand, float* z_out, void* stream) {
-  NWX_REQUIRE(rays && t_vals && z_out && ray_dim >= 8 && S >= 2 && N >= 0);
-  if (N == 0) return NWX_OK;
+  NWX_REQUIRE(ray_dim >= 8 && S >= 2 && N >= 0);
+  if (N == 0) return NWX_OK;                     // empty shard: pointers may be null
+  NWX_REQUIRE(rays && t_vals && z_out);
   const int64_t total = N * S;
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)nwx::num_sms() * 16;
@@ -160,8 +163,9 @@ extern "C" int nwx_coarse_z(const float* rays, int ray_dim, int64_t N, int S, co
 }
 
 extern "C" int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream) {
-  NWX_REQUIRE(x && out && n >= 0);
+  NWX_REQUIRE(n >= 0);
   if (n == 0) return NWX_OK;
+  NWX_REQUIRE(x && out);
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)nwx::num_sms() * 16;
   if (blocks > cap) blocks = cap;

@@ -219,9 +219,9 @@ static inline unsigned pdf_grid(int64_t N) {
 extern "C" int nwx_sample_pdf(const float* z_c, const float* w_c, int Sc, const float* u, const float* u_lin,
                               int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds,
                               float* z_std, void* stream) {
-  NWX_REQUIRE(z_c && w_c && z_samples && (u || u_lin) && N >= 0);
-  NWX_REQUIRE(Sc >= 11 && Sc <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
+  NWX_REQUIRE(N >= 0 && Sc >= 11 && Sc <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
   if (N == 0) return NWX_OK;
+  NWX_REQUIRE(z_c && w_c && z_samples && (u || u_lin));
   nwx::sample_pdf_kernel<true><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
       z_c, w_c, Sc, Sc - 1, u, u_lin, n_imp, N, z_samples, z_fine, inds, z_std, nullptr);
   NWX_LAUNCHED();
@@ -231,9 +231,9 @@ extern "C" int nwx_sample_pdf(const float* z_c, const float* w_c, int Sc, const 
 extern "C" int nwx_sample_pdf_bins(const float* bins, const float* weights, int M, const float* u,
                                    const float* u_lin, int n_imp, int64_t N, float* samples, int64_t* inds,
                                    float* cdf_out, void* stream) {
-  NWX_REQUIRE(bins && weights && samples && (u || u_lin) && N >= 0);
-  NWX_REQUIRE(M >= 10 && M <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
+  NWX_REQUIRE(N >= 0 && M >= 10 && M <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
   if (N == 0) return NWX_OK;
+  NWX_REQUIRE(bins && weights && samples && (u || u_lin));
   nwx::sample_pdf_kernel<false><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
       bins, weights, 0, M, u, u_lin, n_imp, N, samples, nullptr, inds, nullptr, cdf_out);
   NWX_LAUNCHED();

@@ -7,6 +7,7 @@ dmjovan/NeRF-Workspaces-Explorer, behind the reference's own Python entry points
 Everything computes in hand-written CUDA kernels loaded through the C ABI of libnwx.so
 (include/nwx.h); importing the package without the built library is fine, calling into it is
 an error (there is no fallback path)."""
+from . import config, dist, synthetic                                     # noqa: F401
 from ._lib import NwxError, build, lib                                     # noqa: F401
 from .batch_utils import batchify, batchify_rays                           # noqa: F401
 from .camera_poses import get_camera_poses_from_list_of_coordinates        # noqa: F401
@@ -17,5 +18,8 @@ from .models import (Embedding, NeRFModel, img2mse, mse2psnr, raw2outputs, run_n
                      to8b, to8b_np)
 from .rays import create_rays, sample_pdf                                  # noqa: F401
 from .training import NeRFReplicaTrainingHandler, Trainer                  # noqa: F401
+
+from .workspace import (OfficeBelgradeWorkspace, OfficeGeneveWorkspace, OfficeNewYorkWorkspace,   # noqa: F401
+                        OfficeTokyoWorkspace, Workspace)
 
 __version__ = "0.1.0"

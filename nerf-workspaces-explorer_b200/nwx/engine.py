@@ -298,7 +298,7 @@ def embed(x: torch.Tensor, num_freqs: int, scalar_factor: float) -> torch.Tensor
     out = torch.empty((flat.shape[0], 3 + 6 * num_freqs), device=x.device)
     check(_lib.lib().nwx_embed(flat.data_ptr(), flat.shape[0], num_freqs, float(scalar_factor), out.data_ptr(),
                                _stream()), "nwx_embed")
-    return out.reshape(*lead, -1)
+    return out.reshape(*lead, 3 + 6 * num_freqs)
 
 
 def to8b(x: torch.Tensor) -> torch.Tensor:

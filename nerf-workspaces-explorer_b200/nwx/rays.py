@@ -15,7 +15,7 @@ def create_rays(num_images: int, Ts_c2w: torch.Tensor, height: int, width: int, 
         raise ValueError(f"num_images={num_images} but {Ts_c2w.shape[0]} poses given")
     eng = _engine_for(device)
     rays = eng.raygen(Ts_c2w, height, width, fx, fy, cx, cy, near, far, use_view_dirs)
-    return rays.view(num_images, height * width, -1)
+    return rays.view(num_images, height * width, 11 if use_view_dirs else 8)
 
 
 def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, N_samples: int, det: bool = False,

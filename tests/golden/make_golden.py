@@ -247,6 +247,22 @@ def main():
         gsmall[k + ".norm"] = v.double().norm()
         gsmall[k + ".sub"] = v.reshape(-1)[::97].clone()
     save("train_grads", **gsmall)
+    # ---- the caller above the path: Workspace coordinate transforms (application/workspace.py) ----
+    from application import workspace as ref_ws
+    sys.path.insert(0, os.path.join(ROOT, "nerf-workspaces-explorer_b200"))
+    import nwx.workspace as my_ws
+    cases = [(0.0, 0.0, 0, 0), (1.0, 1.0, 30, -30), (0.25, 0.7, 330, 30), (0.5, 0.5, 90, 0)]
+    packs = {}
+    for cls in ("OfficeTokyoWorkspace", "OfficeNewYorkWorkspace", "OfficeGeneveWorkspace", "OfficeBelgradeWorkspace"):
+        r, m = getattr(ref_ws, cls)(), getattr(my_ws, cls)()
+        rows = []
+        for c in cases:
+            a, b = r._transform_relative_coordinates(*c), m._transform_relative_coordinates(*c)
+            assert tuple(a[0]) == tuple(b[0]) and tuple(a[1]) == tuple(b[1]), (cls, c)
+            rows.append(list(a[0]) + list(a[1]))
+        assert r.name == m.name and tuple(r.floor_plan_scale) == tuple(m.floor_plan_scale)
+        packs[cls] = np.array(rows)
+    save("workspace", cases=np.array(cases, dtype=np.float64), **packs)
     print("golden vectors written; oracle == reference bit-exactly on every case")
 
 

@@ -117,3 +117,21 @@ def test_drop_in_modules_on_cpu(nwx_mod):
     assert torch.equal(out, torch.arange(10.) * 2)
     parts = nwx_mod.batchify_rays(lambda r: {"a": r[:, 0]}, torch.arange(20.).reshape(10, 2), chunk=4)
     assert torch.equal(parts["a"], torch.arange(0., 20., 2))
+
+
+def test_workspace_transforms_match_reference(nwx_mod):
+    """application/workspace.py:91-196: floor-plan click -> (camera COORD, view COORD), all 4 rooms."""
+    import numpy as np
+    from conftest import GOLDEN
+    import nwx.workspace as ws
+    g = np.load(os.path.join(GOLDEN, "workspace.npz"))
+    for cls in ("OfficeTokyoWorkspace", "OfficeNewYorkWorkspace", "OfficeGeneveWorkspace", "OfficeBelgradeWorkspace"):
+        w = getattr(ws, cls)()
+        for case, ref in zip(g["cases"], g[cls]):
+            init, view = w._transform_relative_coordinates(float(case[0]), float(case[1]), int(case[2]), int(case[3]))
+            assert list(init) + list(view) == list(ref), (cls, case)
+    assert repr(ws.OfficeGeneveWorkspace()) == "Office Geneve" and ws.OfficeGeneveWorkspace().floor_plan_scale == (600, 1000)
+    with pytest.raises(KeyError):
+        ws.Workspace("Office Atlantis")
+    with pytest.raises(RuntimeError, match="cannot be found"):
+        ws.OfficeTokyoWorkspace().initialize_models()              # no checkpoint shipped: reference behaviour

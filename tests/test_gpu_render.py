@@ -135,3 +135,78 @@ def test_full_frame_properties_640x480():
     assert float((full["rgb_fine"][idx.to(DEV)].cpu() - ref["rgb_fine"]).abs().max()) <= 1e-3
     assert float((full["acc_fine"][idx.to(DEV)].cpu() - ref["acc_fine"]).abs().max()) <= 1e-3
     assert float((full["depth_fine"][idx.to(DEV)].cpu() - ref["depth_fine"]).abs().max()) <= 1e-3 * DEPTH_RANGE
+
+
+def test_empty_and_ragged_inputs(handler):
+    """Edge cases: zero rays through every entry point (an empty shard is legal), one ray, and a
+    ray count that is not a multiple of any tile size."""
+    import nwx
+    from nwx import engine as E
+    eng = handler.engine
+    z0 = torch.empty((0, 64), device=DEV)
+    rays0 = torch.empty((0, 11), device=DEV)
+    assert eng.coarse_z(rays0, 64).shape == (0, 64)
+    assert eng.mlp_forward(E.COARSE, rays0, z0).shape == (0, 64, 4)
+    assert eng.mlp_forward_points(E.COARSE, torch.empty((0, 3), device=DEV), torch.empty((0, 3), device=DEV)).shape == (0, 4)
+    assert E.composite(torch.empty((0, 64, 4), device=DEV), z0, torch.empty((0, 3), device=DEV))[0].shape == (0, 3)
+    assert E.sample_pdf_merge(z0, z0, 128)[1].shape == (0, 192)
+    assert E.embed(torch.empty((0, 3), device=DEV), 10, 10.0).shape == (0, 63)
+    assert E.to8b(torch.empty((0, 3), device=DEV)).shape == (0, 3)
+    out = eng.render_rays(rays0, want=orc.REFERENCE_KEYS)
+    assert out["rgb_fine"].shape == (0, 3) and out["raw_fine"].shape == (0, 192, 4)
+    g = load_golden("render_infer")
+    one = handler._volumetric_rendering(g["rays"][:1].to(DEV))
+    odd = handler._volumetric_rendering(g["rays"][:37].to(DEV))
+    assert torch.equal(one["rgb_fine"], odd["rgb_fine"][:1])
+    assert float((odd["rgb_fine"].cpu() - g["rgb_fine"][:37]).abs().max()) <= 1e-3
+
+
+def test_config1_160x120_view_vs_oracle():
+    """BASELINE.json configs[0]: one 160x120 view (19 200 rays, 64+128 samples), the whole frame against
+    the CPU oracle: rgb within 1e-3, PSNR reported against the fp32 render, uint8 image within one level."""
+    import nwx
+    sd_c, sd_f = _nets()
+    H, W = 120, 160
+    fx, fy, cx, cy = orc.intrinsics(H, W)
+    pose = orc.synthetic_poses(36, 0)[14:15]
+    h = nwx.NeRFReplicaInferenceHandler("office_tokyo", None)
+    h.load_state_dicts(sd_c, sd_f)
+    h._img_h, h._img_w, h._n_pix, h._fx, h._fy, h._cx, h._cy = H, W, H * W, fx, fy, cx, cy
+    img = h.render_poses(pose)[0]
+    rays = nwx.create_rays(1, pose, H, W, fx, fy, cx, cy, 0.1, 10.0)[0]
+    mine = h._render_rays(rays)
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    with torch.no_grad():
+        ref = orc.render_rays(rays.cpu(), sd_c, sd_f, orc.RenderConfig(), keys=("rgb_fine", "acc_fine", "depth_fine"))
+    err = (mine["rgb_fine"].cpu() - ref["rgb_fine"]).abs()
+    mse = float((err ** 2).mean())
+    psnr = -10 * math.log10(max(mse, 1e-20))
+    print(f"config 1: max |rgb| err {float(err.max()):.2e}, PSNR vs fp32 reference {psnr:.1f} dB")
+    assert float(err.max()) <= 1e-3 and psnr > 70.0
+    assert float((mine["acc_fine"].cpu() - ref["acc_fine"]).abs().max()) <= 1e-3
+    assert float((mine["depth_fine"].cpu() - ref["depth_fine"]).abs().max()) <= 1e-3 * DEPTH_RANGE
+    ref_img = orc.to8b(ref["rgb_fine"].numpy().reshape(H, W, 3))
+    assert int(np.abs(img.astype(int) - ref_img.astype(int)).max()) <= 1
+
+
+def test_workspace_render_image_from_checkpoint(tmp_path):
+    """The caller above the path: Workspace.render_image (application/workspace.py:54-68) from a
+    checkpoint file in the reference's shipped key style (no leading underscore)."""
+    import nwx
+    sd_c, sd_f = _nets()
+    path = str(tmp_path / "model.ckpt")
+    torch.save({"global_step": 0, "network_coarse_state_dict": {k[1:]: v for k, v in sd_c.items()},
+                "network_fine_state_dict": {k[1:]: v for k, v in sd_f.items()}, "optimizer_state_dict": {}}, path)
+    cfg = nwx.config.default_config()
+    cfg["experiment"].update(image_height=24, image_width=32)
+    ws = nwx.OfficeTokyoWorkspace(ckpt_path=path, config=cfg)
+    ws.initialize_models()
+    img = ws.render_image(0.4, 0.6, 30, 0)
+    assert img.shape == (24, 32, 3) and img.dtype == np.uint8
+    init, view = ws._transform_relative_coordinates(0.4, 0.6, 30, 0)
+    pose = nwx.get_camera_poses_from_list_of_coordinates(init, [view])
+    fx, fy, cx, cy = orc.intrinsics(24, 32)
+    ref = orc.render_image(pose, sd_c, sd_f, orc.RenderConfig(), 24, 32, fx, fy, cx, cy, 0.1, 10.0)
+    assert int(np.abs(img.astype(int) - ref.astype(int)).max()) <= 1
+    sweep = ws.render_sweep(0.4, 0.6, horizontal_angles=(0, 30), vertical_angles=(0,))
+    assert sweep.shape == (2, 24, 32, 3) and np.array_equal(sweep[1], img)
