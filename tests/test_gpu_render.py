@@ -210,3 +210,29 @@ def test_workspace_render_image_from_checkpoint(tmp_path):
     assert int(np.abs(img.astype(int) - ref.astype(int)).max()) <= 1
     sweep = ws.render_sweep(0.4, 0.6, horizontal_angles=(0, 30), vertical_angles=(0,))
     assert sweep.shape == (2, 24, 32, 3) and np.array_equal(sweep[1], img)
+
+
+def test_trained_like_weights_stress():
+    """SURVEY.md section 8d stress set: sigma head x30, rgb head x10, sigma bias 1.0 -- dense, saturated
+    fields like a trained scene, where bf16 hidden activations are amplified most.  Reported and
+    bounded: rgb within 2e-3, acc within 5e-3 (the sigma head is scaled x30), PSNR vs the fp32 reference
+    > 55 dB.  (The 1e-3 bar of the north star is met on the standard weights, tests above.)"""
+    import nwx
+    from nwx import engine as E
+    gen = torch.Generator().manual_seed(7)
+    sd_c = orc.init_state_dict(7, trained_like=True, generator=gen)
+    sd_f = orc.init_state_dict(7, trained_like=True, generator=gen)
+    eng = nwx.Engine(torch.device(DEV))
+    eng.load_weights(E.COARSE, sd_c); eng.load_weights(E.FINE, sd_f)
+    fx, fy, cx, cy = orc.intrinsics(24, 32)
+    rays = orc.create_rays(1, orc.synthetic_poses(36, 0)[20:21], 24, 32, fx, fy, cx, cy, 0.1, 10.0)[0]
+    out = eng.render_rays(rays.to(DEV), want=("rgb_fine", "rgb_coarse", "acc_fine", "depth_fine"))
+    with torch.no_grad():
+        ref = orc.volumetric_rendering(rays, sd_c, sd_f, orc.RenderConfig(), train_mode=False)
+    err = (out["rgb_fine"].cpu() - ref["rgb_fine"]).abs()
+    psnr = -10 * math.log10(max(float((err ** 2).mean()), 1e-20))
+    print(f"trained-like: max |rgb_fine| err {float(err.max()):.2e}, |rgb_coarse| "
+          f"{float((out['rgb_coarse'].cpu() - ref['rgb_coarse']).abs().max()):.2e}, PSNR {psnr:.1f} dB, "
+          f"depth err {float((out['depth_fine'].cpu() - ref['depth_fine']).abs().max()):.2e} m")
+    assert float(err.max()) <= 2e-3 and psnr > 55.0
+    assert float((out["acc_fine"].cpu() - ref["acc_fine"]).abs().max()) <= 5e-3
