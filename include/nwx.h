@@ -37,6 +37,8 @@ enum {
   NWX_E_INVALID = 1,      /* bad argument (null pointer, unsupported size)          */
   NWX_E_NO_WEIGHTS = 2,   /* nwx_load_weights was not called for the requested net  */
   NWX_E_UNSUPPORTED = 3,  /* device is not sm_100 (there is no fallback path)        */
+  NWX_E_STALE = 4,        /* nwx_train_pack ran after the last nwx_load_weights: the inference
+                             entry points need nwx_load_weights again (host-side biases)  */
   NWX_E_CUDA = 1000       /* 1000 + cudaError_t                                      */
 };
 

@@ -80,6 +80,7 @@ extern "C" const char* nwx_error_string(int code) {
     case NWX_E_INVALID: return "invalid argument";
     case NWX_E_NO_WEIGHTS: return "weights not loaded (call nwx_load_weights)";
     case NWX_E_UNSUPPORTED: return "device is not sm_100 (B200); there is no fallback path";
+    case NWX_E_STALE: return "weights were trained since the last nwx_load_weights: reload them before inference";
     default:
       if (code >= NWX_E_CUDA) return cudaGetErrorString((cudaError_t)(code - NWX_E_CUDA));
       return "unknown error";
@@ -174,6 +175,7 @@ static int run_mlp(nwx_ctx* ctx, int which, const float* rays, int ray_dim, cons
                    float* raw_out, cudaStream_t st, const float* embedded = nullptr, cudaEvent_t mid = nullptr) {
   const nwx::PackedNet& net = ctx->net[which];
   if (!net.loaded) return NWX_E_NO_WEIGHTS;
+  if (net.consts_stale) return NWX_E_STALE;      // trained since the last nwx_load_weights: biases on the host are old
   int rc = nwx::launch_dirbias(net, dirs, dir_stride, n_dir, embedded != nullptr, dirbias, st);
   if (rc) return rc;
   if (mid) NWX_CUDA_TRY(cudaEventRecord(mid, st));
@@ -227,6 +229,7 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin));
   if (N == 0) return NWX_OK;
   if (!ctx->net[0].loaded || !ctx->net[1].loaded) return NWX_E_NO_WEIGHTS;
+  if (ctx->net[0].consts_stale || ctx->net[1].consts_stale) return NWX_E_STALE;
   auto st = (cudaStream_t)stream;
   const int Sc = o->n_samples, Ni = o->n_importance, Sf = Sc + Ni, rd = o->ray_dim;
   const ScratchPlan pl = plan_scratch(N, Sc, Ni);

@@ -522,6 +522,7 @@ int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
   NWX_CUDA_TRY(cudaMemcpyAsync(c.b_rgb, t[23], sizeof(float) * 3, cudaMemcpyDeviceToHost, st));
   NWX_CUDA_TRY(cudaStreamSynchronize(st));       // load-time only: the consts are a host-side launch argument
   net.loaded = true;
+  net.consts_stale = false;
   return NWX_OK;
 }
 

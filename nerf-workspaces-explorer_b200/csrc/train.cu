@@ -314,6 +314,13 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
+          // the next step's ReLU mask (this row's two 128 B lines of the saved activation image):
+          // pull it into L2 now, one MMA step ahead, so the epilogue's loads do not wait on DRAM
+          if (s + 1 < kDxSteps && tile < args.n_tiles) {
+            const uint8_t* nm = args.acts + tile_img_offset(act_slot_kb0(8 - s), 4, args.n_tiles, tile, wg * 2) + row * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nm));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + kTileImgBytes));
+          }
         }
       }
     }

@@ -84,9 +84,9 @@ class Trainer:
 
     def sync_inference_weights(self) -> None:
         """Refresh the engine's inference-side copy (host constants) from the master parameters."""
-        self.engine.load_weights(COARSE, self.state_dict(COARSE))
+        self.pack()                                              # training-side images / device constants
+        self.engine.load_weights(COARSE, self.state_dict(COARSE))   # host-side constants (clears the stale mark)
         self.engine.load_weights(FINE, self.state_dict(FINE))
-        self.pack()
 
     # ---- checkpoints (reference format, training handler:394-409) ---------------------------------
     def checkpoint(self, global_step: int) -> Dict[str, object]:

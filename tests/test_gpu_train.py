@@ -120,6 +120,8 @@ def test_training_trajectory_vs_oracle_and_inference_sync():
     sd = tr.state_dict(0)
     assert list(sd) == list(orc.STATE_KEYS) and sd["_pts_linears.5.weight"].shape == (256, 319)
     assert float((sd["_rgb_linear.bias"].cpu() - pc["_rgb_linear.bias"]).abs().max()) <= 2e-4     # same Adam trajectory
+    with pytest.raises(nwx.NwxError, match="trained since"):      # inference on stale host-side biases is refused
+        eng.render_rays(rays.to(DEV), want=("rgb_fine",))
     tr.sync_inference_weights()
     out = eng.render_rays(rays.to(DEV), want=("rgb_fine",))["rgb_fine"]
     mse = float(((out.cpu() - gt) ** 2).mean())
