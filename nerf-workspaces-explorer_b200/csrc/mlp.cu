@@ -370,6 +370,12 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (lane == 0 && quad == 0) trace(3 + wg, 12, it, l, t);
           const uint32_t d_tmem = lane_addr + t * kHidden;
           const int64_t p = tile_of(it, t) * kTileM + row;
+          if (kTrain) {
+            // the TMA store that saved this buffer's previous contents must have finished reading it
+            // (groups complete in order: all but the newest one, which belongs to the other tile)
+            if (warp == 8 && lane == 0) bulk_wait_read<1>();
+            named_bar_sync(3, 256);
+          }
           float* tap_row = nullptr;
           if (kTap && args.dbg_out != nullptr && args.dbg_layer == l && p < P) tap_row = args.dbg_out + p * kHidden;
           if (kTap && args.dbg_layer == -4 && args.dbg_out != nullptr) {
@@ -377,21 +383,15 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           } else if (l < 9) {
             const uint32_t hrow = (kTap && args.dbg_layer == -3 && args.dbg_out != nullptr)
                                       ? 0u : sbase + L::h0 + t * kHBytes + row * 128;
-            const bool save = kTrain && args.acts != nullptr && tile_of(it, t) < args.n_tiles;
-            uint8_t* grow = save ? args.acts + tile_img_offset(act_slot_kb0(l + 1), 4, args.n_tiles, tile_of(it, t), 0) + row * 128
-                                 : nullptr;
             if (l == 7) {
-              const float sig = save ? epilogue_hidden<kEpiReluSigma, kTap, true>(cst, l, d_tmem, hrow, row, wg, tap_row, grow)
-                                     : epilogue_hidden<kEpiReluSigma, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
+              const float sig = epilogue_hidden<kEpiReluSigma, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
               if (t == 0) sig0 = sig; else sig1 = sig;
             } else if (l == 8) {
-              if (save) epilogue_hidden<kEpiLinear, kTap, true>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
-              else epilogue_hidden<kEpiLinear, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
+              epilogue_hidden<kEpiLinear, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
             } else {
-              if (save) epilogue_hidden<kEpiRelu, kTap, true>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
-              else epilogue_hidden<kEpiRelu, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, grow);
+              epilogue_hidden<kEpiRelu, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
             }
-            fence_proxy_async_smem();            // my smem writes -> visible to the next layer's UMMA
+            fence_proxy_async_smem();            // my smem writes -> visible to the next layer's UMMA / TMA store
           } else {
             // views layer (N = 128): + (b_view + W_view[:,256:] . pe(dir)), ReLU, fp32 rgb head
             const int64_t pc = p < P ? p : P - 1;
@@ -443,9 +443,18 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             else mbar_arrive(sbase + L::a_ready + 8 * t);
             if (quad == 0) trace(3 + wg, 13, it, l, t);
           }
+          if (kTrain && l < 9) {
+            // training: the activation tile just written IS the image the backward wants -- one TMA
+            // store of the whole 64 KB tile instead of 16 global stores per thread
+            named_bar_sync(3, 256);              // every warp's tile writes are fenced
+            if (warp == 8 && lane == 0 && args.acts != nullptr && tile_of(it, t) < args.n_tiles)
+              bulk_s2g(args.acts + tile_img_offset(act_slot_kb0(l + 1), 4, args.n_tiles, tile_of(it, t), 0),
+                       sbase + L::h0 + t * kHBytes, kHBytes);
+          }
         }
       }
     }
+    if (kTrain && warp == 8 && lane == 0) bulk_wait_read<0>();   // smem must outlive the last store's reads
   }
 
   // --------------------------------------------------------------- teardown ----

@@ -97,8 +97,8 @@ struct DxArgs {
 enum { kBwdLinear = 0, kBwdSigmaMask = 1, kBwdMask = 2 };
 
 template <int kKind>
-__device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tmem, uint32_t hrow, bool to_smem, int row,
-                                             int wg, const uint8_t* mrow, uint8_t* grow, float dsig) {
+__device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tmem, uint32_t hrow, bool to_smem, bool to_gmem,
+                                             int row, int wg, const uint8_t* mrow, uint8_t* grow, float dsig) {
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
     const int col = wg * 128 + cc * 32;
@@ -131,7 +131,7 @@ __device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tm
     for (int q = 0; q < 4; ++q) {
       const uint32_t off = kbo + (((j0 + q) ^ (row & 7)) << 4);
       if (to_smem) st_shared_v4(hrow + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      if (to_gmem) *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     }
   }
 }
@@ -307,13 +307,25 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           // mask = activation that the produced gradient flows into: step 1 -> h8 (act slot 8) ... step 8 -> h1
           const int64_t mt = tile < args.n_tiles ? tile : 0;
           const uint8_t* mrow = args.acts + tile_img_offset(act_slot_kb0(s == 0 ? 9 : 9 - s), 4, args.n_tiles, mt, 0) + row * 128;
-          if (s == 0) bwd_epilogue<kBwdLinear>(cst, d_tmem, hrow, true, row, wg, mrow, grow, 0.f);
-          else if (s == 1) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, row, wg, mrow, grow, dsig[t]);
-          else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, row, wg, mrow, grow, 0.f);
+          // Steps 0..6 leave their G tile in smem (next step's A operand) and save it with ONE TMA
+          // store; steps 7 and 8 store per thread: after step 8's MMA the G_views producers reuse the
+          // buffer, and they cannot wait on another thread's bulk group.
+          const bool via_tma = s < kDxSteps - 2;
+          if (warp == 8 && lane == 0) bulk_wait_read<1>();      // earlier store of this buffer has finished reading it
+          named_bar_sync(3, 256);
+          if (s == 0) bwd_epilogue<kBwdLinear>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, 0.f);
+          else if (s == 1) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, dsig[t]);
+          else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, !via_tma, row, wg, mrow, grow, 0.f);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
+          if (via_tma) {
+            named_bar_sync(3, 256);                             // every warp's tile writes are fenced
+            if (warp == 8 && lane == 0)
+              bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 1), 4, args.n_tiles + 1, wt, 0),
+                       sbase + L::h0 + t * kHBytes, kHBytes);
+          }
           // the next step's ReLU mask (this row's two 128 B lines of the saved activation image):
           // pull it into L2 now, one MMA step ahead, so the epilogue's loads do not wait on DRAM
           if (s + 1 < kDxSteps && tile < args.n_tiles) {
@@ -324,6 +336,7 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
         }
       }
     }
+    if (warp == 8 && lane == 0) bulk_wait_read<0>();            // smem must outlive the last store's reads
   }
   tc_fence_before();
   cluster_sync();
