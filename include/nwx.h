@@ -146,6 +146,13 @@ typedef struct nwx_render_opts {
   const float* u;         /* [N,n_importance] or NULL = det (rays.py:95-98) */
   const float* noise_coarse; /* [N,n_samples] scaled, or NULL  (model_utils.py:65) */
   const float* noise_fine;   /* [N,n_samples+n_importance] scaled, or NULL */
+  /* In-kernel random source (counter-based Philox, csrc/rng.cuh) for the draws above whose pointer
+   * is NULL -- nothing is stored in HBM and the backward regenerates the forward's noise: */
+  uint64_t rng_seed;         /* key                                                             */
+  uint64_t rng_offset;       /* e.g. the step number: fresh numbers every step                  */
+  float raw_noise_std;       /* > 0 and noise_* == NULL: sigma noise N(0,1)*std generated in place */
+  int rng_jitter;            /* != 0 and t_rand == NULL: stratified jitter generated in place     */
+  int rng_u;                 /* != 0 and u == NULL: random importance uniforms (else deterministic) */
 } nwx_render_opts;
 
 typedef struct nwx_render_out {       /* any pointer may be NULL = not wanted, except rgb_fine */
@@ -164,6 +171,12 @@ int nwx_ctx_reserve(nwx_ctx* ctx, int64_t max_rays, int n_samples, int n_importa
 /* inference handler:203-277 / training handler:534-618 for N rays [N,ray_dim]. */
 int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const nwx_render_opts* opts,
                     const nwx_render_out* out, void* stream);
+
+/* out[i] = the library's counter-based draw for element i of (seed, offset, rng_stream): kind 0 =
+ * U[0,1), kind 1 = N(0,1)*scale.  rng_stream: 0 jitter, 1 importance u, 2 / 3 sigma noise of the
+ * coarse / fine pass.  Exactly what the kernels generate in place (tests inject it back as tensors). */
+int nwx_rng_fill(int kind, uint64_t seed, uint64_t offset, uint32_t rng_stream, float scale, int64_t n,
+                 float* out, void* stream);
 
 /* (255*clip(x,0,1)).astype(uint8) (model_utils.py:9) over n floats. */
 int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream);

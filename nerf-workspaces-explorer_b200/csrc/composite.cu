@@ -49,8 +49,8 @@ struct RaySample {
 // Loads chunk j of a ray and evaluates the per-sample terms of model_utils.py:49-71.
 template <int K>
 __device__ __forceinline__ void load_ray(const float* __restrict__ raw, const float* __restrict__ z,
-                                         const float* __restrict__ noise, int64_t ray, int S, int lane,
-                                         float dnorm, RaySample (&sm)[K]) {
+                                         const float* __restrict__ noise, const RngSpec& rng, int64_t ray, int S,
+                                         int lane, float dnorm, RaySample (&sm)[K]) {
   float zr[K];
   float4 rw[K];
   float nz[K];
@@ -61,8 +61,9 @@ __device__ __forceinline__ void load_ray(const float* __restrict__ raw, const fl
     const int64_t idx = ray * S + (ok ? s : S - 1);
     zr[j] = ldg_stream(z + idx);
     rw[j] = ldg_stream4(reinterpret_cast<const float4*>(raw) + idx);
-    nz[j] = noise ? ldg_stream(noise + idx) : 0.0f;
+    nz[j] = noise ? ldg_stream(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
   }
+  const bool noisy = noise != nullptr || rng.on;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const int s = j * 32 + lane;
@@ -71,7 +72,7 @@ __device__ __forceinline__ void load_ray(const float* __restrict__ raw, const fl
     if (lane == 31) znext = zhead;
     float dist = (s >= S - 1) ? 1e10f : __fsub_rn(znext, zr[j]);          // :51,:56
     dist = __fmul_rn(dist, dnorm);                                        // :60
-    const float sg = noise ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
+    const float sg = noisy ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
     const float r = fmaxf(sg, 0.0f);
     const float e = expf(__fmul_rn(-r, dist));                            // :49
     RaySample& o = sm[j];
@@ -96,7 +97,7 @@ template <int K>
 __global__ void __launch_bounds__(kCompWarps * 32, 4)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
-                     int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
+                     const RngSpec rng, int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
                      float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
                      int32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
@@ -115,8 +116,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const int64_t idx = ray * S + (s < S ? s : S - 1);
       zr[j] = ldg_stream(z + idx);
       rw[j] = ldg_stream4(reinterpret_cast<const float4*>(raw) + idx);
-      nz[j] = noise ? ldg_stream(noise + idx) : 0.0f;
+      nz[j] = noise ? ldg_stream(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
     }
+    const bool noisy = noise != nullptr || rng.on;
     const float dnorm = ray_dnorm(rays_d, d_stride, ray);
     double carry = 1.0;
     float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
@@ -128,7 +130,7 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       if (lane == 31) znext = zhead;
       float dist = (s >= S - 1) ? 1e10f : __fsub_rn(znext, zr[j]);          // :51,:56
       dist = __fmul_rn(dist, dnorm);                                        // :60
-      const float sg = noise ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
+      const float sg = noisy ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
       float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg, 0.0f), dist)));   // :49
       float t = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);                   // :75
       if (s >= S) { alpha = 0.0f; t = 1.0f; }                               // padding lanes: neutral
@@ -180,14 +182,14 @@ template <int K>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
-                     const float* __restrict__ d_rgb, int64_t N, int S, int white_bkgd,
+                     const RngSpec rng, const float* __restrict__ d_rgb, int64_t N, int S, int white_bkgd,
                      float* __restrict__ d_raw) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
   for (int64_t ray = warp0; ray < N; ray += nwarps) {
     RaySample sm[K];
-    load_ray<K>(raw, z, noise, ray, S, lane, ray_dnorm(rays_d, d_stride, ray), sm);
+    load_ray<K>(raw, z, noise, rng, ray, S, lane, ray_dnorm(rays_d, d_stride, ray), sm);
     const float g0 = __ldg(d_rgb + ray * 3 + 0), g1 = __ldg(d_rgb + ray * 3 + 1), g2 = __ldg(d_rgb + ray * 3 + 2);
     const float gbg = white_bkgd ? (g0 + g1 + g2) : 0.0f;
     float T[K], w[K], G[K];
@@ -246,30 +248,42 @@ static inline unsigned comp_grid(int64_t N) {
     default: return NWX_E_INVALID;                    \
   }
 
+int nwx::launch_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
+                              const RngSpec& rng, int64_t N, int S, int white_bkgd, float* rgb, float* disp, float* acc,
+                              float* depth, float* weights, int32_t* flags, cudaStream_t st) {
+  NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
+  if (N == 0) return NWX_OK;
+  NWX_REQUIRE(raw && z && rays_d && rgb);
+  NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
+                        raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags)));
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+int nwx::launch_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
+                              const RngSpec& rng, const float* d_rgb, int64_t N, int S, int white_bkgd, float* d_raw,
+                              cudaStream_t st) {
+  NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
+  if (N == 0) return NWX_OK;
+  NWX_REQUIRE(raw && z && rays_d && d_rgb && d_raw);
+  NWX_DISPATCH_K(S, (nwx::composite_bwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
+                        raw, z, rays_d, d_stride, noise, rng, d_rgb, N, S, white_bkgd, d_raw)));
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
 extern "C" int nwx_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
                                  const float* noise, int64_t N, int S, int white_bkgd, float* rgb,
                                  float* disp, float* acc, float* depth, float* weights, int32_t* flags,
                                  void* stream) {
-  NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
-  if (N == 0) return NWX_OK;
-  NWX_REQUIRE(raw && z && rays_d && rgb);
-  auto st = (cudaStream_t)stream;
-  NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
-                        raw, z, rays_d, d_stride, noise, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags)));
-  NWX_LAUNCHED();
-  return NWX_OK;
+  return nwx::launch_composite_fwd(raw, z, rays_d, d_stride, noise, nwx::RngSpec{}, N, S, white_bkgd, rgb, disp, acc,
+                                   depth, weights, flags, (cudaStream_t)stream);
 }
 
 extern "C" int nwx_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,
                                  const float* noise, const float* weights, const float* d_rgb, int64_t N,
                                  int S, int white_bkgd, float* d_raw, void* stream) {
   (void)weights;   // recomputed from raw: cheaper than re-reading 4 B/sample and exact for alpha = 0
-  NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
-  if (N == 0) return NWX_OK;
-  NWX_REQUIRE(raw && z && rays_d && d_rgb && d_raw);
-  auto st = (cudaStream_t)stream;
-  NWX_DISPATCH_K(S, (nwx::composite_bwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
-                        raw, z, rays_d, d_stride, noise, d_rgb, N, S, white_bkgd, d_raw)));
-  NWX_LAUNCHED();
-  return NWX_OK;
+  return nwx::launch_composite_bwd(raw, z, rays_d, d_stride, noise, nwx::RngSpec{}, d_rgb, N, S, white_bkgd, d_raw,
+                                   (cudaStream_t)stream);
 }

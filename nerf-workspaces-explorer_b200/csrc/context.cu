@@ -38,6 +38,16 @@ struct nwx_ctx {
 
 namespace {
 
+// The random source of one draw: the caller's tensor if given, else the library's counter-based
+// generator when the options ask for it (rng_* fields), else none.
+nwx::RngSpec rng_for(const nwx_render_opts* o, uint32_t stream_id, const float* tensor, bool wanted) {
+  nwx::RngSpec r;
+  r.seed = o->rng_seed; r.offset = o->rng_offset; r.stream = stream_id;
+  r.scale = stream_id >= 2 ? o->raw_noise_std : 1.0f;
+  r.on = (tensor == nullptr && wanted) ? 1 : 0;
+  return r;
+}
+
 struct ScratchPlan {
   size_t z_c, raw_c, w_c, z_s, z_f, raw_f, dirbias, rgb_c, rgb_f, total;
 };
@@ -226,7 +236,7 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   if (N == 0) return NWX_OK;
   NWX_REQUIRE(rays && out->rgb_fine);
   NWX_REQUIRE(o->n_samples >= 11 && o->n_samples <= 128 && o->n_importance >= 1 && o->n_importance <= 128);
-  NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin));
+  NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin || o->rng_u));
   if (N == 0) return NWX_OK;
   if (!ctx->net[0].loaded || !ctx->net[1].loaded) return NWX_E_NO_WEIGHTS;
   if (ctx->net[0].consts_stale || ctx->net[1].consts_stale) return NWX_E_STALE;
@@ -253,21 +263,24 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   };
 
   if ((rc = mark(0))) return rc;
-  if ((rc = nwx_coarse_z(rays, rd, N, Sc, o->t_vals, o->t_rand, z_c, st))) return rc;
+  const nwx::RngSpec rj = rng_for(o, 0, o->t_rand, o->rng_jitter != 0), ru = rng_for(o, 1, o->u, o->rng_u != 0);
+  const nwx::RngSpec rnc = rng_for(o, 2, o->noise_coarse, o->raw_noise_std > 0.f);
+  const nwx::RngSpec rnf = rng_for(o, 3, o->noise_fine, o->raw_noise_std > 0.f);
+  if ((rc = nwx::launch_coarse_z(rays, rd, N, Sc, o->t_vals, o->t_rand, rj, z_c, st))) return rc;
   if ((rc = mark(1))) return rc;
   if ((rc = run_mlp(ctx, NWX_NET_COARSE, rays, rd, z_c, nullptr, rays + 8, rd, N, N * Sc, Sc, dirb, raw_c, st, nullptr,
                     prof ? ctx->ev[2] : nullptr))) return rc;
   if ((rc = mark(3))) return rc;
-  if ((rc = nwx_composite_fwd(raw_c, z_c, rays + 3, rd, o->noise_coarse, N, Sc, o->white_bkgd, rgb_c, out->disp_coarse,
-                              out->acc_coarse, out->depth_coarse, w_c, out->flags, st))) return rc;
+  if ((rc = nwx::launch_composite_fwd(raw_c, z_c, rays + 3, rd, o->noise_coarse, rnc, N, Sc, o->white_bkgd, rgb_c,
+                                      out->disp_coarse, out->acc_coarse, out->depth_coarse, w_c, out->flags, st))) return rc;
   if ((rc = mark(4))) return rc;
-  if ((rc = nwx_sample_pdf(z_c, w_c, Sc, o->u, o->u_lin, Ni, N, z_s, z_f, out->inds, out->z_std, st))) return rc;
+  if ((rc = nwx::launch_sample_pdf(z_c, w_c, Sc, o->u, ru, o->u_lin, Ni, N, z_s, z_f, out->inds, out->z_std, st))) return rc;
   if ((rc = mark(5))) return rc;
   if ((rc = run_mlp(ctx, NWX_NET_FINE, rays, rd, z_f, nullptr, rays + 8, rd, N, N * Sf, Sf, dirb, raw_f, st, nullptr,
                     prof ? ctx->ev[6] : nullptr))) return rc;
   if ((rc = mark(7))) return rc;
-  if ((rc = nwx_composite_fwd(raw_f, z_f, rays + 3, rd, o->noise_fine, N, Sf, o->white_bkgd, out->rgb_fine, out->disp_fine,
-                              out->acc_fine, out->depth_fine, out->weights_fine, out->flags, st))) return rc;
+  if ((rc = nwx::launch_composite_fwd(raw_f, z_f, rays + 3, rd, o->noise_fine, rnf, N, Sf, o->white_bkgd, out->rgb_fine,
+                                      out->disp_fine, out->acc_fine, out->depth_fine, out->weights_fine, out->flags, st))) return rc;
   if (out->rgb8_fine && (rc = nwx_to8b(out->rgb_fine, N * 3, out->rgb8_fine, st))) return rc;
   if ((rc = mark(8))) return rc;
   ctx->ev_recorded = prof;
@@ -326,7 +339,7 @@ TrainPlan plan_train(int64_t N, int Sc, int Ni) {
 extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N, const nwx_render_opts* o, void* stream) {
   NWX_REQUIRE(ctx && io && o && io->rays && io->gt_rgb && io->grad_coarse && io->grad_fine && io->loss && N > 0);
   NWX_REQUIRE(o->n_samples >= 11 && o->n_samples <= 128 && o->n_importance >= 1 && o->n_importance <= 128);
-  NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin));
+  NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin || o->rng_u));
   for (int w = 0; w < 2; ++w)
     if (!ctx->net[w].loaded || !ctx->net[w].gconsts || !ctx->net[w].wimg_t) return NWX_E_NO_WEIGHTS;   // nwx_train_pack first
   auto st = (cudaStream_t)stream;
@@ -374,20 +387,23 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     a.acts = acts[which]; a.hv_out = hv[which]; a.P = N * S; a.ray_dim = rd; a.S = S;
     return nwx::launch_mlp_train_forward(net, a, st);
   };
-  if ((rc = nwx_coarse_z(io->rays, rd, N, Sc, o->t_vals, o->t_rand, z_c, st))) return rc;
+  const nwx::RngSpec rj = rng_for(o, 0, o->t_rand, o->rng_jitter != 0), ru = rng_for(o, 1, o->u, o->rng_u != 0);
+  const nwx::RngSpec rnc = rng_for(o, 2, o->noise_coarse, o->raw_noise_std > 0.f);
+  const nwx::RngSpec rnf = rng_for(o, 3, o->noise_fine, o->raw_noise_std > 0.f);
+  if ((rc = nwx::launch_coarse_z(io->rays, rd, N, Sc, o->t_vals, o->t_rand, rj, z_c, st))) return rc;
   if ((rc = fwd(NWX_NET_COARSE, z_c, Sc, raw_c))) return rc;
-  if ((rc = nwx_composite_fwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, N, Sc, o->white_bkgd, rgb_c, nullptr, nullptr,
-                              nullptr, w_c, nullptr, st))) return rc;
-  if ((rc = nwx_sample_pdf(z_c, w_c, Sc, o->u, o->u_lin, Ni, N, z_s, z_f, nullptr, nullptr, st))) return rc;
+  if ((rc = nwx::launch_composite_fwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, rnc, N, Sc, o->white_bkgd, rgb_c,
+                                      nullptr, nullptr, nullptr, w_c, nullptr, st))) return rc;
+  if ((rc = nwx::launch_sample_pdf(z_c, w_c, Sc, o->u, ru, o->u_lin, Ni, N, z_s, z_f, nullptr, nullptr, st))) return rc;
   if ((rc = fwd(NWX_NET_FINE, z_f, Sf, raw_f))) return rc;
-  if ((rc = nwx_composite_fwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, N, Sf, o->white_bkgd, rgb_f, nullptr, nullptr,
-                              nullptr, nullptr, nullptr, st))) return rc;
+  if ((rc = nwx::launch_composite_fwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, rnf, N, Sf, o->white_bkgd, rgb_f,
+                                      nullptr, nullptr, nullptr, nullptr, nullptr, st))) return rc;
   // ---- loss (training handler:291-305) and backward through compositing; z_samples is detached (:580) ----
   if ((rc = nwx::launch_mse_grad(rgb_c, rgb_f, io->gt_rgb, N, d_rgb[0], d_rgb[1], io->loss, st))) return rc;
-  if ((rc = nwx_composite_bwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, nullptr, d_rgb[0], N, Sc, o->white_bkgd,
-                              d_raw[0], st))) return rc;
-  if ((rc = nwx_composite_bwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, nullptr, d_rgb[1], N, Sf, o->white_bkgd,
-                              d_raw[1], st))) return rc;
+  if ((rc = nwx::launch_composite_bwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, rnc, d_rgb[0], N, Sc, o->white_bkgd,
+                                      d_raw[0], st))) return rc;
+  if ((rc = nwx::launch_composite_bwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, rnf, d_rgb[1], N, Sf, o->white_bkgd,
+                                      d_raw[1], st))) return rc;
   if ((rc = nwx::launch_embed(io->rays + 8, rd, N, 4, 1.0f, pe_dir, st))) return rc;   // pe(viewdir) per ray
   // ---- backward through the two MLPs ----
   float* grads[2] = {io->grad_coarse, io->grad_fine};

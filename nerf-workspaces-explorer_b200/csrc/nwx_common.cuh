@@ -6,6 +6,7 @@
 #include <atomic>
 
 #include "../../include/nwx.h"
+#include "rng.cuh"
 
 #define NWX_CUDA_TRY(expr)                                   \
   do {                                                       \
@@ -62,6 +63,18 @@ inline int num_sms() {
   }
   return n;
 }
+
+// Internal launchers with an optional in-kernel random source (rng.on) in place of the tensors
+int launch_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals, const float* t_rand,
+                    const RngSpec& rng, float* z_out, cudaStream_t st);
+int launch_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
+                         const RngSpec& rng, int64_t N, int S, int white_bkgd, float* rgb, float* disp, float* acc,
+                         float* depth, float* weights, int32_t* flags, cudaStream_t st);
+int launch_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
+                         const RngSpec& rng, const float* d_rgb, int64_t N, int S, int white_bkgd, float* d_raw,
+                         cudaStream_t st);
+int launch_sample_pdf(const float* z_c, const float* w_c, int Sc, const float* u, const RngSpec& rng, const float* u_lin,
+                      int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds, float* z_std, cudaStream_t st);
 
 // Embedding.embed on rows of stride x_stride (rays.cu)
 int launch_embed(const float* x, int x_stride, int64_t P, int num_freqs, float scalar_factor, float* out,

@@ -56,7 +56,7 @@ raygen_kernel(const float* __restrict__ c2w, int H, int W, float fx, float fy, f
 
 __global__ void __launch_bounds__(256)
 coarse_z_kernel(const float* __restrict__ rays, int ray_dim, int64_t total, int S,
-                const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                const float* __restrict__ t_vals, const float* __restrict__ t_rand, const RngSpec rng,
                 float* __restrict__ z_out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -68,10 +68,11 @@ coarse_z_kernel(const float* __restrict__ rays, int ray_dim, int64_t total, int 
       return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
     };
     float z = zlin(s);
-    if (t_rand != nullptr) {                                    // training handler:555-562
+    if (t_rand != nullptr || rng.on) {                          // training handler:555-562
       const float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zlin(s - 1)));
       const float upper = (s == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zlin(s + 1), z));
-      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), ldg_stream(t_rand + i)));
+      const float tr = t_rand ? ldg_stream(t_rand + i) : rng_uniform(rng, (uint64_t)i);
+      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
     }
     z_out[i] = z;
   }
@@ -147,8 +148,8 @@ extern "C" int nwx_raygen(const float* c2w, int B, int H, int W, float fx, float
   return NWX_OK;
 }
 
-extern "C" int nwx_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals,
-                            const float* t_rand, float* z_out, void* stream) {
+int nwx::launch_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals, const float* t_rand,
+                         const RngSpec& rng, float* z_out, cudaStream_t st) {
   NWX_REQUIRE(ray_dim >= 8 && S >= 2 && N >= 0);
   if (N == 0) return NWX_OK;                     // empty shard: pointers may be null
   NWX_REQUIRE(rays && t_vals && z_out);
@@ -156,8 +157,36 @@ extern "C" int nwx_coarse_z(const float* rays, int ray_dim, int64_t N, int S, co
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)nwx::num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  nwx::coarse_z_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rays, ray_dim, total, S, t_vals,
-                                                                         t_rand, z_out);
+  nwx::coarse_z_kernel<<<(unsigned)blocks, 256, 0, st>>>(rays, ray_dim, total, S, t_vals, t_rand, rng, z_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+extern "C" int nwx_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals,
+                            const float* t_rand, float* z_out, void* stream) {
+  return nwx::launch_coarse_z(rays, ray_dim, N, S, t_vals, t_rand, nwx::RngSpec{}, z_out, (cudaStream_t)stream);
+}
+
+// Fills out[i] with the library's counter-based draws (kind 0: U[0,1), 1: N(0,1)*scale) for element
+// index i of (seed, offset, stream): what the kernels generate in place when no tensor is injected.
+namespace nwx {
+__global__ void __launch_bounds__(256)
+rng_fill_kernel(int kind, RngSpec rng, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = kind == 0 ? rng_uniform(rng, (uint64_t)i) : rng_normal(rng, (uint64_t)i);
+}
+}  // namespace nwx
+
+extern "C" int nwx_rng_fill(int kind, uint64_t seed, uint64_t offset, uint32_t rng_stream, float scale, int64_t n,
+                            float* out, void* stream) {
+  NWX_REQUIRE((kind == 0 || kind == 1) && n >= 0);
+  if (n == 0) return NWX_OK;
+  NWX_REQUIRE(out);
+  nwx::RngSpec r;
+  r.seed = seed; r.offset = offset; r.stream = rng_stream; r.scale = scale; r.on = 1;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)nwx::num_sms() * 16) blocks = (int64_t)nwx::num_sms() * 16;
+  nwx::rng_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kind, r, n, out);
   NWX_LAUNCHED();
   return NWX_OK;
 }

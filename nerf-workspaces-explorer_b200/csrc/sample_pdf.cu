@@ -97,8 +97,8 @@ __device__ __forceinline__ void warp_bitonic_sort(float* a, int n2, int lane) {
 template <bool kFromCoarse>
 __global__ void __launch_bounds__(kPdfWarps * 32)
 sample_pdf_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int Sc, int M,
-                  const float* __restrict__ u, const float* __restrict__ u_lin, int n_imp, int64_t N,
-                  float* __restrict__ z_samples, float* __restrict__ z_fine, int64_t* __restrict__ inds_out,
+                  const float* __restrict__ u, const RngSpec rng, const float* __restrict__ u_lin, int n_imp,
+                  int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, int64_t* __restrict__ inds_out,
                   float* __restrict__ z_std, float* __restrict__ cdf_out) {
   __shared__ PdfSmem smem[kPdfWarps];
   PdfSmem& sm = smem[threadIdx.x >> 5];
@@ -106,7 +106,7 @@ sample_pdf_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
   const int64_t warp0 = (int64_t)blockIdx.x * kPdfWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kPdfWarps;
   const int nw = M - 1;                                         // number of pdf weights
-  const bool det = (u == nullptr);
+  const bool det = (u == nullptr) && !rng.on;
 
   for (int64_t ray = warp0; ray < N; ray += nwarps) {
     // ---- stage inputs ----
@@ -150,7 +150,8 @@ sample_pdf_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       const int q = base + lane;
       float smp = 0.f;
       if (q < n_imp) {
-        const float uu = det ? __ldg(u_lin + q) : ldg_stream(u + ray * n_imp + q);
+        const float uu = det ? __ldg(u_lin + q)
+                             : (u ? ldg_stream(u + ray * n_imp + q) : rng_uniform(rng, (uint64_t)(ray * n_imp + q)));
         const int ind = upper_bound(sm.cdf, M, uu);                                   // :103 right=True
         const int below = max(ind - 1, 0), above = min(ind, M - 1);                   // :104-105
         const float cb = sm.cdf[below], ca = sm.cdf[above];
@@ -216,16 +217,23 @@ static inline unsigned pdf_grid(int64_t N) {
 
 }  // namespace nwx
 
+int nwx::launch_sample_pdf(const float* z_c, const float* w_c, int Sc, const float* u, const RngSpec& rng,
+                           const float* u_lin, int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds,
+                           float* z_std, cudaStream_t st) {
+  NWX_REQUIRE(N >= 0 && Sc >= 11 && Sc <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
+  if (N == 0) return NWX_OK;
+  NWX_REQUIRE(z_c && w_c && z_samples && (u || u_lin || rng.on));
+  nwx::sample_pdf_kernel<true><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, st>>>(
+      z_c, w_c, Sc, Sc - 1, u, rng, u_lin, n_imp, N, z_samples, z_fine, inds, z_std, nullptr);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
 extern "C" int nwx_sample_pdf(const float* z_c, const float* w_c, int Sc, const float* u, const float* u_lin,
                               int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds,
                               float* z_std, void* stream) {
-  NWX_REQUIRE(N >= 0 && Sc >= 11 && Sc <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
-  if (N == 0) return NWX_OK;
-  NWX_REQUIRE(z_c && w_c && z_samples && (u || u_lin));
-  nwx::sample_pdf_kernel<true><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
-      z_c, w_c, Sc, Sc - 1, u, u_lin, n_imp, N, z_samples, z_fine, inds, z_std, nullptr);
-  NWX_LAUNCHED();
-  return NWX_OK;
+  return nwx::launch_sample_pdf(z_c, w_c, Sc, u, nwx::RngSpec{}, u_lin, n_imp, N, z_samples, z_fine, inds, z_std,
+                                (cudaStream_t)stream);
 }
 
 extern "C" int nwx_sample_pdf_bins(const float* bins, const float* weights, int M, const float* u,
@@ -235,7 +243,7 @@ extern "C" int nwx_sample_pdf_bins(const float* bins, const float* weights, int 
   if (N == 0) return NWX_OK;
   NWX_REQUIRE(bins && weights && samples && (u || u_lin));
   nwx::sample_pdf_kernel<false><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
-      bins, weights, 0, M, u, u_lin, n_imp, N, samples, nullptr, inds, nullptr, cdf_out);
+      bins, weights, 0, M, u, nwx::RngSpec{}, u_lin, n_imp, N, samples, nullptr, inds, nullptr, cdf_out);
   NWX_LAUNCHED();
   return NWX_OK;
 }

@@ -20,7 +20,9 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 class RenderOpts(C.Structure):
     _fields_ = [("n_samples", _i), ("n_importance", _i), ("white_bkgd", _i), ("ray_dim", _i),
                 ("t_vals", _vp), ("u_lin", _vp), ("t_rand", _vp), ("u", _vp),
-                ("noise_coarse", _vp), ("noise_fine", _vp)]
+                ("noise_coarse", _vp), ("noise_fine", _vp),
+                ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64), ("raw_noise_std", _f),
+                ("rng_jitter", _i), ("rng_u", _i)]
 
 
 RENDER_OUT_FIELDS = ("rgb_coarse", "disp_coarse", "acc_coarse", "depth_coarse", "raw_coarse",
@@ -63,6 +65,7 @@ PROTOTYPES = {
     "nwx_ctx_set_profiling": (_i, [_vp, _i]),
     "nwx_ctx_stage_ms": (_i, [_vp, C.POINTER(_f)]),
     "nwx_render_rays": (_i, [_vp, _vp, _i64, C.POINTER(RenderOpts), C.POINTER(RenderOut), _vp]),
+    "nwx_rng_fill": (_i, [_i, C.c_uint64, C.c_uint64, C.c_uint32, _f, _i64, _vp, _vp]),
     "nwx_to8b": (_i, [_vp, _i64, _vp, _vp]),
     "nwx_launch_count": (_i64, []),
     "nwx_set_mlp_variant": (_i, [_vp, _i]),

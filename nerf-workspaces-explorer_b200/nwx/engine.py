@@ -90,6 +90,29 @@ def normalize_state_dict(sd: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tens
     return out
 
 
+class RngOptions:
+    """In-kernel random draws (counter-based Philox keyed by seed/offset) for the training-mode
+    render: stratified jitter, random importance uniforms, sigma noise N(0,1)*noise_std."""
+
+    def __init__(self, seed: int = 0, offset: int = 0, jitter: bool = False, random_u: bool = False,
+                 noise_std: float = 0.0):
+        self.seed, self.offset, self.jitter, self.random_u, self.noise_std = seed, offset, jitter, random_u, noise_std
+
+    def fields(self):
+        return (self.seed & 0xFFFFFFFFFFFFFFFF, self.offset & 0xFFFFFFFFFFFFFFFF, float(self.noise_std),
+                int(self.jitter), int(self.random_u))
+
+
+def rng_fill(kind: str, seed: int, offset: int, stream: int, n: int, scale: float = 1.0,
+             device: Optional[torch.device] = None) -> torch.Tensor:
+    """The library's draws as a tensor: kind 'uniform' | 'normal'; stream 0 jitter, 1 u, 2/3 noise."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n,), device=dev)
+    check(_lib.lib().nwx_rng_fill({"uniform": 0, "normal": 1}[kind], seed, offset, stream, float(scale), n,
+                                  out.data_ptr(), _stream()), "nwx_rng_fill")
+    return out
+
+
 class Engine:
     """One nwx_ctx: bf16-packed coarse+fine weights and scratch on one GPU."""
 
@@ -202,10 +225,12 @@ class Engine:
                     white_bkgd: bool = False, want: Iterable[str] = REFERENCE_KEYS,
                     t_rand: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None,
                     noise_coarse: Optional[torch.Tensor] = None, noise_fine: Optional[torch.Tensor] = None,
-                    out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                    out: Optional[Dict[str, torch.Tensor]] = None, rng: Optional["RngOptions"] = None
+                    ) -> Dict[str, torch.Tensor]:
         """The body of _volumetric_rendering for all rays at once (inference handler:203-277;
         with t_rand/u/noise_*: training handler:534-618).  `want` selects output tensors; only
-        those are written to HBM.  Adds "flags" (int32: bit0 NaN, bit1 Inf)."""
+        those are written to HBM.  Adds "flags" (int32: bit0 NaN, bit1 Inf).  `rng` switches on the
+        in-kernel counter-based draws for whichever of t_rand / u / noise_* is not given."""
         rays = _f32(rays, "rays")
         N, dev = rays.shape[0], rays.device
         want = set(want) | {"rgb_fine"}
@@ -216,9 +241,10 @@ class Engine:
                                      dtype=_OUT_DTYPES.get(k, torch.float32))
         res["flags"] = torch.zeros(1, device=dev, dtype=torch.int32)
         keep = [None if t is None else _f32(t, "rand") for t in (t_rand, u, noise_coarse, noise_fine)]
+        rng = rng or RngOptions()
         opts = RenderOpts(n_samples, n_importance, int(white_bkgd), rays.shape[1],
                           linspace01(n_samples, dev).data_ptr(), linspace01(n_importance, dev).data_ptr(),
-                          _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]))
+                          _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), *rng.fields())
         outs = RenderOut(*[_ptr(res.get(name)) for name in RENDER_OUT_FIELDS])
         check(self._lib.nwx_render_rays(self._ctx, rays.data_ptr(), N, C.byref(opts), C.byref(outs), _stream()),
               "nwx_render_rays")

@@ -47,7 +47,7 @@ class Trainer:
                  lr: float = 5e-4, lr_decay_rate: float = 0.1, lr_decay_steps: int = 50000,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, n_samples: int = 64,
                  n_importance: int = 128, white_bkgd: bool = False, perturb: float = 1.0, raw_noise_std: float = 1.0,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, seed: int = 0):
         self.engine, self.device, self.group = eng, eng.device, group
         self.lr0, self.lr, self.lr_decay_rate, self.lr_decay_steps = lr, lr, lr_decay_rate, lr_decay_steps
         self.betas, self.eps = betas, eps
@@ -63,6 +63,7 @@ class Trainer:
         self.v = torch.zeros_like(self.params)
         self.loss = torch.zeros(2, device=self.device, dtype=torch.float64)
         self.opt_steps = 0
+        self.seed, self.draws = seed, 0          # in-kernel RNG key and per-call offset
         self.pack()
 
     # ---- parameters ------------------------------------------------------------------------
@@ -137,20 +138,18 @@ class Trainer:
                          noise_fine: Optional[torch.Tensor] = None, want_rgb: bool = False):
         """Render `rays` in training mode, loss = mse(rgb_c, gt) + mse(rgb_f, gt), gradients into
         self.grads.  The three random draws of the reference (t_rand training handler:560, noise
-        model_utils.py:65, u rays.py:98) are taken on the device unless injected."""
+        model_utils.py:65, u rays.py:98) are generated inside the kernels (counter-based, keyed by the
+        trainer's seed and a per-call offset) unless tensors are injected."""
         rays, gt = _f32(rays, "rays"), _f32(gt_rgb, "gt_rgb")
         N, dev = rays.shape[0], rays.device
         Sc, Ni = self.n_samples, self.n_importance
-        if t_rand is None and self.perturb > 0.:
-            t_rand = torch.rand((N, Sc), device=dev)
-        if u is None and self.perturb > 0.:
-            u = torch.rand((N, Ni), device=dev)
-        if noise_coarse is None and self.raw_noise_std > 0.:
-            noise_coarse = torch.randn((N, Sc), device=dev) * self.raw_noise_std
-            noise_fine = torch.randn((N, Sc + Ni), device=dev) * self.raw_noise_std
         keep = [None if t is None else _f32(t, "rand") for t in (t_rand, u, noise_coarse, noise_fine)]
+        rng = _engine.RngOptions(self.seed, self.draws, jitter=self.perturb > 0., random_u=self.perturb > 0.,
+                                 noise_std=self.raw_noise_std if self.raw_noise_std > 0. else 0.0)
+        self.draws += 1
         opts = RenderOpts(Sc, Ni, int(self.white_bkgd), rays.shape[1], linspace01(Sc, dev).data_ptr(),
-                          linspace01(Ni, dev).data_ptr(), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]))
+                          linspace01(Ni, dev).data_ptr(), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]),
+                          *rng.fields())
         rgb_c = torch.empty((N, 3), device=dev) if want_rgb else None
         rgb_f = torch.empty((N, 3), device=dev) if want_rgb else None
         io = TrainIO(rays.data_ptr(), gt.data_ptr(), self.grads[COARSE].data_ptr(), self.grads[FINE].data_ptr(),
@@ -203,7 +202,7 @@ class NeRFReplicaTrainingHandler:
                                lr_decay_steps=int(trn["learning_rate_decay_steps"]),
                                n_samples=int(rnd["n_samples"]), n_importance=int(rnd["n_importance"]),
                                white_bkgd=bool(rnd["white_background"]), perturb=float(rnd["perturb"]),
-                               raw_noise_std=float(rnd["raw_noise_std"]))
+                               raw_noise_std=float(rnd["raw_noise_std"]), seed=seed)
         self._gen = torch.Generator(device=dev).manual_seed(seed)
 
     def _sample_training_data(self):

@@ -172,3 +172,48 @@ def test_checkpoint_round_trip_reference_format(tmp_path):
     tr.step(rays, gt, 2); tr2.step(rays, gt, 2)
     assert torch.equal(tr.m != 0, tr2.m != 0)
     assert float((tr.params - tr2.params).abs().max()) <= 1e-6
+
+
+def test_in_kernel_rng_statistics_and_equivalence():
+    """The counter-based draws: (a) sane distributions, reproducible, fresh per offset; (b) generating
+    them inside the kernels is bit-identical to injecting the same numbers as tensors."""
+    import nwx
+    from nwx import engine as E
+    n = 1 << 20
+    uni = E.rng_fill("uniform", 7, 3, 0, n).cpu()
+    nor = E.rng_fill("normal", 7, 3, 2, n, scale=2.0).cpu()
+    assert float(uni.min()) >= 0.0 and float(uni.max()) < 1.0
+    assert abs(float(uni.mean()) - 0.5) < 2e-3 and abs(float(uni.var()) - 1 / 12) < 1e-3
+    hist = torch.histc(uni, bins=16, min=0, max=1) / n
+    assert float((hist - 1 / 16).abs().max()) < 2e-3
+    assert abs(float(nor.mean())) < 1e-2 and abs(float(nor.std()) - 2.0) < 1e-2
+    assert abs(float((nor.abs() < 2.0).float().mean()) - 0.6827) < 3e-3
+    assert torch.equal(uni, E.rng_fill("uniform", 7, 3, 0, n).cpu())
+    assert not torch.equal(uni, E.rng_fill("uniform", 7, 4, 0, n).cpu())
+    assert abs(float(torch.corrcoef(torch.stack([uni[:-1], uni[1:]]))[0, 1])) < 5e-3
+
+    eng = nwx.Engine(torch.device(DEV))
+    sd_c, sd_f = _nets()
+    eng.load_weights(E.COARSE, sd_c); eng.load_weights(E.FINE, sd_f)
+    g = load_golden("render_train")
+    rays = g["rays"].to(DEV)
+    N = rays.shape[0]
+    seed, off, std = 11, 5, 1.0
+    t_rand = E.rng_fill("uniform", seed, off, 0, N * 64).view(N, 64)
+    u = E.rng_fill("uniform", seed, off, 1, N * 128).view(N, 128)
+    nc = E.rng_fill("normal", seed, off, 2, N * 64, scale=std).view(N, 64)
+    nf = E.rng_fill("normal", seed, off, 3, N * 192, scale=std).view(N, 192)
+    want = ("rgb_coarse", "rgb_fine", "z_vals_coarse", "z_vals_fine", "depth_fine")
+    a = eng.render_rays(rays, want=want, t_rand=t_rand, u=u, noise_coarse=nc, noise_fine=nf)
+    b = eng.render_rays(rays, want=want, rng=E.RngOptions(seed, off, jitter=True, random_u=True, noise_std=std))
+    for k in want:
+        assert torch.equal(a[k], b[k]), k
+    assert not torch.equal(a["rgb_fine"], eng.render_rays(rays, want=want)["rgb_fine"])      # the draws matter
+    # and through the trainer: in-kernel draws == injected tensors (gradients to atomics' rounding)
+    tr = nwx.Trainer(nwx.Engine(torch.device(DEV)), sd_c, sd_f, seed=seed)
+    tr.draws = off
+    gt = g["gt"].float().to(DEV)
+    l1 = tr.forward_backward(rays, gt).clone(); g1 = tr.grads.clone()
+    l2 = tr.forward_backward(rays, gt, t_rand, u, nc, nf).clone(); g2 = tr.grads.clone()
+    assert torch.equal(l1, l2)
+    assert float((g1 - g2).abs().max()) <= 1e-6 * float(g2.abs().max())

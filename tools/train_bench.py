@@ -36,7 +36,7 @@ def main():
     eng = nwx.Engine(dev)
     bank = eng.raygen(synthetic.sweep_poses(36, 0), H, W, fx, fy, cx, cy, 0.1, 10.0)        # [36*H*W, 11] ray bank
     gen = torch.Generator(device=dev).manual_seed(2 + rank)
-    tr = nwx.Trainer(eng, *synthetic.random_state_dicts(0))
+    tr = nwx.Trainer(eng, *synthetic.random_state_dicts(0), seed=2 + rank)
 
     def batch():
         idx = torch.randint(0, bank.shape[0], (args.rays,), device=dev, generator=gen)
