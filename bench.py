@@ -165,6 +165,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
     import nwx
     from nwx import engine as E
+    from nwx.dist import gather_tiles, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -184,14 +185,13 @@ def run_gpu_arm(args):
     handler._cx, handler._cy = cx, cy
     handler.load_state_dicts(sd_c, sd_f)
     eng = handler.engine
-    n_local = H * W                                   # one frame's worth of the batch per rank
+    batch_poses = poses[:world]                       # the step's global batch: one view per GPU
+    total_rays = world * H * W
+    ray0, n_local = shard_range(total_rays, rank, world)   # contiguous ray range of this rank (nwx/dist.py)
     eng.reserve(n_local, N_SAMPLES, N_IMPORTANCE)
     eng.set_profiling(True)
-
-    batch_poses = poses[:world]                       # the step's global batch: one view per GPU
-    rays = eng.raygen(batch_poses, H, W, fx, fy, cx, cy, NEAR, FAR, True, ray0=rank * n_local, nrays=n_local)
+    rays = eng.raygen(batch_poses, H, W, fx, fy, cx, cy, NEAR, FAR, True, ray0=ray0, nrays=n_local)
     rgb8 = torch.empty((n_local, 3), device=dev, dtype=torch.uint8)
-    gathered = torch.empty((world * n_local, 3), device=dev, dtype=torch.uint8) if world > 1 else rgb8
     pinned_pose = batch_poses[rank:rank + 1].clone().pin_memory()
 
     def barrier():
@@ -201,8 +201,7 @@ def run_gpu_arm(args):
 
     def device_step():
         eng.render_rays(rays, N_SAMPLES, N_IMPORTANCE, False, want=("rgb8_fine",), out={"rgb8_fine": rgb8})
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, rgb8)
+        return gather_tiles(rgb8, total_rays)          # NCCL all-gather of the uint8 pixel tiles (identity at N=1)
 
     def e2e_step():
         img = handler.render_poses(pinned_pose)       # H2D pose, render, D2H uint8 frame (public API)
