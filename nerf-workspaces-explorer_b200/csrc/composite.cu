@@ -33,7 +33,7 @@ __device__ __forceinline__ double warp_incl_sum(double v, int lane) {
 }
 
 __device__ __forceinline__ float sigmoidf_rn(float x) {        // torch.sigmoid: 1/(1+exp(-x))
-  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+  return __frcp_rn(__fadd_rn(1.0f, expf(-x)));                 // correctly rounded 1/y == correctly rounded reciprocal
 }
 
 struct RaySample {

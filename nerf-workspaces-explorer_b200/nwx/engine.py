@@ -235,6 +235,14 @@ class Engine:
         N, dev = rays.shape[0], rays.device
         want = set(want) | {"rgb_fine"}
         res = dict(out) if out else {}
+        unknown = [k for k in set(want) | set(res) if k not in _OUT_SHAPES]
+        if unknown:
+            raise _lib.NwxError(f"render_rays: unknown output(s) {sorted(unknown)}; known: {sorted(_OUT_SHAPES)}")
+        for k, t in res.items():                  # caller-provided outputs are written in place: validate them
+            shape, dtype = _OUT_SHAPES[k](N, n_samples, n_importance), _OUT_DTYPES.get(k, torch.float32)
+            if not (t.is_cuda and t.device == dev and t.is_contiguous() and t.dtype == dtype and tuple(t.shape) == shape):
+                raise _lib.NwxError(f"render_rays: out[{k!r}] must be a contiguous {dtype} CUDA tensor of shape {shape} "
+                                    f"on {dev}, got {t.dtype} {tuple(t.shape)} on {t.device}")
         for k in want:
             if k not in res:
                 res[k] = torch.empty(_OUT_SHAPES[k](N, n_samples, n_importance), device=dev,

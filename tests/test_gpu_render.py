@@ -154,6 +154,13 @@ def test_empty_and_ragged_inputs(handler):
     assert E.to8b(torch.empty((0, 3), device=DEV)).shape == (0, 3)
     out = eng.render_rays(rays0, want=orc.REFERENCE_KEYS)
     assert out["rgb_fine"].shape == (0, 3) and out["raw_fine"].shape == (0, 192, 4)
+    with pytest.raises(nwx.NwxError, match="unknown output"):
+        eng.render_rays(rays0, want=("rgb_fine", "not_a_key"))
+    with pytest.raises(nwx.NwxError, match="contiguous"):
+        eng.render_rays(torch.zeros((4, 11), device=DEV), want=("rgb_fine",),
+                        out={"rgb_fine": torch.zeros((4, 6), device=DEV)[:, ::2]})
+    with pytest.raises(nwx.NwxError, match="CUDA tensor"):
+        eng.render_rays(torch.zeros((4, 11)))
     g = load_golden("render_infer")
     one = handler._volumetric_rendering(g["rays"][:1].to(DEV))
     odd = handler._volumetric_rendering(g["rays"][:37].to(DEV))
