@@ -26,6 +26,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The tests exercise the in-tree libnwx.so; build it (same Makefile as __graft_entry__.build()) if a
+    fresh checkout does not have it yet.  There is still no fallback: a failed build fails the session."""
+    import nwx
+    if not os.path.exists(nwx._lib.LIB_PATH):
+        nwx.build()
+    yield
+
+
 def load_golden(name):
     """Fixture written by tests/golden/make_golden.py from the reference's own outputs."""
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
