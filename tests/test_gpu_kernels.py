@@ -165,3 +165,21 @@ def test_composite_backward_vs_autograd():
         got = E.composite_backward(raw.detach().to(DEV), z.to(DEV), d.to(DEV), d_rgb.to(DEV), noise.to(DEV), wb).cpu()
         ref = raw.grad
         assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max())), (S, wb)
+
+
+@pytest.mark.parametrize("M", [12, 20, 47, 63, 100, 127])
+def test_sample_pdf_bins_general_lengths_bit_exact(M):
+    """The literal sample_pdf for other bin counts than the reference's 63: indices and samples stay
+    bit-exact (the CDF's summation order is reproduced for every row length)."""
+    from nwx import engine as E
+    g = torch.Generator().manual_seed(M)
+    N, n_imp = 3000, 96
+    bins = torch.sort(torch.rand(N, M, generator=g) * 9.9 + 0.1, -1)[0]
+    w = torch.rand(N, M - 1, generator=g) ** 5
+    u = torch.rand(N, n_imp, generator=g)
+    for uu in (None, u):
+        ref_s, ref_i = orc.sample_pdf(bins, w, n_imp, det=uu is None, u=uu, return_inds=True)
+        s, i, cdf = E.sample_pdf_bins(bins.to(DEV), w.to(DEV), n_imp, None if uu is None else uu.to(DEV),
+                                      want_inds=True, want_cdf=True)
+        assert bits_equal(cdf.cpu(), orc.pdf_to_cdf(w))
+        assert torch.equal(i.cpu(), ref_i) and bits_equal(s.cpu(), ref_s)

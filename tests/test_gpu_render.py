@@ -243,3 +243,22 @@ def test_trained_like_weights_stress():
           f"depth err {float((out['depth_fine'].cpu() - ref['depth_fine']).abs().max()):.2e} m")
     assert float(err.max()) <= 2e-3 and psnr > 55.0
     assert float((out["acc_fine"].cpu() - ref["acc_fine"]).abs().max()) <= 5e-3
+
+
+def test_other_sampling_config_32_plus_64():
+    """Not only the shipped 64+128: n_samples = 32, n_importance = 64 through the same kernels."""
+    import nwx
+    from nwx import engine as E
+    sd_c, sd_f = _nets()
+    eng = nwx.Engine(torch.device(DEV))
+    eng.load_weights(E.COARSE, sd_c); eng.load_weights(E.FINE, sd_f)
+    g = load_golden("render_infer")
+    rays = g["rays"]
+    cfg = orc.RenderConfig(n_samples=32, n_importance=64)
+    with torch.no_grad():
+        ref = orc.volumetric_rendering(rays, sd_c, sd_f, cfg, train_mode=False)
+    out = eng.render_rays(rays.to(DEV), 32, 64, False, want=("rgb_fine", "rgb_coarse", "acc_fine", "z_vals_coarse", "raw_fine"))
+    assert out["raw_fine"].shape == (rays.shape[0], 96, 4)
+    assert torch.equal(out["z_vals_coarse"].cpu(), ref["z_vals_coarse"].contiguous())
+    for k in ("rgb_fine", "rgb_coarse", "acc_fine"):
+        assert float((out[k].cpu() - ref[k]).abs().max()) <= 1e-3, k
