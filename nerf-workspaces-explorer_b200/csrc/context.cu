@@ -120,6 +120,7 @@ extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
     if (n.wimg) cudaFree(n.wimg);
     if (n.wdir_t) cudaFree(n.wdir_t);
     if (n.bview) cudaFree(n.bview);
+    if (n.bview_fold) cudaFree(n.bview_fold);
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->tscratch) cudaFree(ctx->tscratch);
@@ -141,7 +142,7 @@ extern "C" int nwx_load_weights(nwx_ctx* ctx, int which, const float* const* ten
 }
 
 extern "C" int nwx_set_mlp_variant(nwx_ctx* ctx, int variant) {
-  NWX_REQUIRE(ctx && variant >= 0 && variant <= 3);
+  NWX_REQUIRE(ctx && variant >= 0 && variant <= 4);
   ctx->mlp_variant = variant;
   return NWX_OK;
 }
@@ -186,7 +187,8 @@ static int run_mlp(nwx_ctx* ctx, int which, const float* rays, int ray_dim, cons
   const nwx::PackedNet& net = ctx->net[which];
   if (!net.loaded) return NWX_E_NO_WEIGHTS;
   if (net.consts_stale) return NWX_E_STALE;      // trained since the last nwx_load_weights: biases on the host are old
-  int rc = nwx::launch_dirbias(net, dirs, dir_stride, n_dir, embedded != nullptr, dirbias, st);
+  int rc = nwx::launch_dirbias(net, dirs, dir_stride, n_dir, embedded != nullptr, nwx::variant_folds(ctx->mlp_variant),
+                               dirbias, st);
   if (rc) return rc;
   if (mid) NWX_CUDA_TRY(cudaEventRecord(mid, st));
   nwx::MlpArgs a{};
@@ -379,7 +381,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
   }
   auto fwd = [&](int which, const float* z, int S, float* raw) -> int {
     const nwx::PackedNet& net = ctx->net[which];
-    int r = nwx::launch_dirbias(net, io->rays + 8, rd, N, false, dirb, st);
+    int r = nwx::launch_dirbias(net, io->rays + 8, rd, N, false, false, dirb, st);
     if (r) return r;
     nwx::MlpArgs a{};
     a.which = which;

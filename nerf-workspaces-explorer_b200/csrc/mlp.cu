@@ -31,12 +31,22 @@
 
 namespace nwx {
 
-// chunk schedule: layer 5 is split so that a chunk never needs more than 4 resident K-blocks
-constexpr int kNumChunks = 11;
-__device__ __forceinline__ int chunk_layer(int c) { return c <= 5 ? c : c - 1; }
+// chunk schedule: layer 5 is split so that a chunk never needs more than 4 resident K-blocks.
+// kFold (inference): the feature layer (l = 8) is folded into the views layer (l = 9) at load time, so a
+// tile runs 9 tensor-core layers = 10 chunks instead of 10 layers = 11 chunks (-11 % MMA work).
+template <bool kFold> __device__ __forceinline__ constexpr int num_chunks() { return kFold ? 10 : 11; }
+template <bool kFold> __device__ __forceinline__ constexpr int layers_per_tile() { return kFold ? 9 : 10; }
+template <bool kFold> __device__ __forceinline__ int chunk_layer(int c) {
+  const int l = c <= 5 ? c : c - 1;
+  return (kFold && l == 8) ? 9 : l;
+}
+// position of a layer in a tile's sequence of accumulator hand-offs (mbarrier phase bookkeeping)
+template <bool kFold> __device__ __forceinline__ int layer_seq(int l) { return (kFold && l == 9) ? 8 : l; }
 __device__ __forceinline__ int chunk_kb0(int c) { return c == 6 ? 1 : 0; }
 __device__ __forceinline__ int chunk_nkb(int c) { return (c == 0 || c == 5) ? 1 : 4; }
+template <bool kFold>
 __device__ __forceinline__ int layer_gkb0(int l) {     // global K-block index of a layer's first K-block
+  if (kFold && l == 9) return kFoldKBlock0;
   return l == 0 ? 0 : (l <= 5 ? 1 + 4 * (l - 1) : 22 + 4 * (l - 6));
 }
 
@@ -162,7 +172,7 @@ __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, ui
   return sig;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst_param) {
   using L = SmemLayout<kPair, kStages>;
@@ -181,6 +191,9 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     }
   };
   constexpr int kCG = kPair ? 2 : 1;
+  constexpr int kNumChunks = num_chunks<kFold>();
+  constexpr int kSeqLen = layers_per_tile<kFold>();      // accumulator hand-offs per tile and iteration
+  static_assert(!(kTrain && kFold), "the training forward keeps the reference's layer structure");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -226,7 +239,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       uint32_t fill = 0;
       for (int it = 0; it < iters; ++it) {
         for (int c = 0; c < kNumChunks; ++c) {
-          const int l = chunk_layer(c);
+          const int l = chunk_layer<kFold>(c);
           const uint32_t bytes = (l == 9 ? kKBlockBytes / 2 : kKBlockBytes) / kCG;
           for (int t = 0; t < (kResident ? 1 : 2); ++t) {
             for (int kb = 0; kb < chunk_nkb(c); ++kb, ++fill) {
@@ -236,7 +249,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
               trace(0, 32, it, l, kb);
               const uint32_t bar = sbase + L::w_full + 8 * stage;
               mbar_arrive_expect_tx(bar, bytes);
-              const uint8_t* src = args.wimg + kblock_offset(layer_gkb0(l) + chunk_kb0(c) + kb) + rank * bytes;
+              const uint8_t* src = args.wimg + kblock_offset(layer_gkb0<kFold>(l) + chunk_kb0(c) + kb) + rank * bytes;
               bulk_g2s(sbase + L::w0 + stage * L::kStageBytes, src, bytes, bar);
             }
           }
@@ -251,16 +264,17 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       if (rank == 0) {
         for (int it = 0; it < iters; ++it) {
           for (int c = 0; c < kNumChunks; ++c) {
-            const int l = chunk_layer(c);
+            const int l = chunk_layer<kFold>(c);
             const int nkb = chunk_nkb(c);
+            const uint32_t seq = (uint32_t)it * kSeqLen + layer_seq<kFold>(l);   // index of this accumulator hand-off
             const bool first_chunk = (c != 6), last_chunk = (c != 5);
             const uint32_t idesc = umma_idesc_bf16(kTileM * kCG, l == 9 ? kViewHidden : kHidden);
             for (int t = 0; t < 2; ++t) {
               trace(1, 1, it, l, t);
               if (first_chunk) {
                 if (l == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
-                // a_ready[t] completes once per layer epilogue: phase index = 10*it + l - 1
-                if (l != 0 || it != 0) mbar_wait(sbase + L::a_ready + 8 * t, (l + 1) & 1, wc);
+                // a_ready[t] completes once per layer epilogue: phase index = seq - 1
+                if (seq != 0) mbar_wait(sbase + L::a_ready + 8 * t, (seq - 1) & 1, wc);
                 tc_fence_after();
               }
               trace(1, 2, it, l, t);
@@ -293,7 +307,8 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
         }
       } else {
         // peer CTA of a pair: relay "my half of the weight K-block has landed" to the leader
-        const uint32_t per_iter = kResident ? kNumKBlocks : 2 * kNumKBlocks;
+        constexpr uint32_t kBlocksPerTile = kFold ? kNumKBlocks - 4 : kNumKBlocks;
+        const uint32_t per_iter = kResident ? kBlocksPerTile : 2 * kBlocksPerTile;
         for (uint32_t n = 0; n < per_iter * (uint32_t)iters; ++n, ++fill) {
           const uint32_t stage = fill % kStages, round = fill / kStages;
           mbar_wait(sbase + L::w_full + 8 * stage, round & 1, wc);
@@ -363,9 +378,11 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     float sig0 = 0.f, sig1 = 0.f;                 // sigma-head partials of tile 0 / tile 1
     for (int it = 0; it < iters; ++it) {
       for (int l = 0; l < kNumLayers; ++l) {
+        if (kFold && l == 8) continue;                         // folded into the views layer
+        const uint32_t seq = (uint32_t)it * kSeqLen + layer_seq<kFold>(l);
         for (int t = 0; t < 2; ++t) {
           if (lane == 0 && quad == 0) trace(3 + wg, 11, it, l, t);
-          mbar_wait(sbase + L::acc_full + 8 * t, l & 1, wc);   // phase index = 10*it + l
+          mbar_wait(sbase + L::acc_full + 8 * t, seq & 1, wc);   // phase index = seq
           tc_fence_after();
           if (lane == 0 && quad == 0) trace(3 + wg, 12, it, l, t);
           const uint32_t d_tmem = lane_addr + t * kHidden;
@@ -499,13 +516,40 @@ __global__ void pack_dir_kernel(const float* __restrict__ wv, float* __restrict_
   }
 }
 
+// Folded views layer (inference): W_fold[j][k] = sum_m W_view[j][m] * W_feature[m][k]  (128 x 256, fp64
+// accumulation, rounded once to fp32 and then to bf16), written as 4 half-size K-block images; and
+// b_fold[j] = b_view[j] + sum_m W_view[j][m] * b_feature[m].  hv = relu(W_fold h8 + b_fold + W_view[:,256:] pe(dir))
+// is the same function as nerf_model.py:64-70 with one bf16 rounding fewer (no rounded `feature`).
+__global__ void pack_fold_kernel(const float* __restrict__ wv, const float* __restrict__ wf,
+                                 const float* __restrict__ bv, const float* __restrict__ bf,
+                                 uint8_t* __restrict__ wimg, float* __restrict__ bview_fold) {
+  const int kb = blockIdx.x;                       // K-block of the folded layer (64 input columns)
+  const int n0 = blockIdx.y * 8;                   // 8 output rows per block
+  constexpr int kIn = kHidden + kPeDir;
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(wimg + kblock_offset(kFoldKBlock0 + kb));
+  for (int e = threadIdx.x; e < 8 * 64; e += blockDim.x) {
+    const int n = n0 + (e >> 6), c = e & 63, k = kb * 64 + c;
+    double acc = 0.0;
+    for (int m = 0; m < kHidden; ++m) acc += (double)wv[(size_t)n * kIn + m] * (double)wf[(size_t)m * kHidden + k];
+    const int chunk = (c >> 3) ^ (n & 7);
+    img[n * 64 + chunk * 8 + (c & 7)] = __float2bfloat16_rn((float)acc);
+  }
+  if (kb == 0 && threadIdx.x < 8) {
+    const int n = n0 + threadIdx.x;
+    double acc = (double)bv[n];
+    for (int m = 0; m < kHidden; ++m) acc += (double)wv[(size_t)n * kIn + m] * (double)bf[m];
+    bview_fold[n] = (float)acc;
+  }
+}
+
 // Device-side part of packing (no host synchronisation): swizzled bf16 K-block images, the transposed
 // fp32 view-direction weights and the views bias.  t: 24 device pointers in state_dict order:
 // pts.{0..7}.{w,b} (0..15), views.{w,b} (16,17), feature (18,19), alpha (20,21), rgb (22,23).
-int pack_network_images(PackedNet& net, const float* const* t, cudaStream_t st) {
+int pack_network_images(PackedNet& net, const float* const* t, bool with_fold, cudaStream_t st) {
   if (!net.wimg) NWX_CUDA_TRY(cudaMalloc(&net.wimg, kWeightImageBytes));
   if (!net.wdir_t) NWX_CUDA_TRY(cudaMalloc(&net.wdir_t, sizeof(float) * kPeDir * kViewHidden));
   if (!net.bview) NWX_CUDA_TRY(cudaMalloc(&net.bview, sizeof(float) * kViewHidden));
+  if (!net.bview_fold) NWX_CUDA_TRY(cudaMalloc(&net.bview_fold, sizeof(float) * kViewHidden));
   PackSrc src;
   for (int i = 0; i < 8; ++i) src.w[i] = t[2 * i];
   src.w[8] = t[18];
@@ -515,11 +559,15 @@ int pack_network_images(PackedNet& net, const float* const* t, cudaStream_t st) 
   pack_dir_kernel<<<4, 256, 0, st>>>(t[16], net.wdir_t);
   NWX_LAUNCHED();
   NWX_CUDA_TRY(cudaMemcpyAsync(net.bview, t[17], sizeof(float) * kViewHidden, cudaMemcpyDeviceToDevice, st));
+  if (with_fold) {
+    pack_fold_kernel<<<dim3(4, kViewHidden / 8), 256, 0, st>>>(t[16], t[18], t[17], t[19], net.wimg, net.bview_fold);
+    NWX_LAUNCHED();
+  }
   return NWX_OK;
 }
 
 int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
-  int rc = pack_network_images(net, t, st);
+  int rc = pack_network_images(net, t, true, st);
   if (rc) return rc;
   MlpConsts& c = net.consts;
   for (int i = 0; i < 8; ++i)
@@ -571,19 +619,19 @@ dirbias_kernel(const float* __restrict__ dirs, int stride, int64_t n, int pre_em
     if (base + r < n) out[(base + r) * kViewHidden + j] = acc[r];
 }
 
-int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, float* out,
-                   cudaStream_t st) {
+int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, bool fold,
+                   float* out, cudaStream_t st) {
   if (n == 0) return NWX_OK;
   dirbias_kernel<<<(unsigned)((n + 7) / 8), kViewHidden, 0, st>>>(dirs, stride, n, pre_embedded ? 1 : 0, net.wdir_t,
-                                                                 net.bview, out);
+                                                                 fold ? net.bview_fold : net.bview, out);
   NWX_LAUNCHED();
   return NWX_OK;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false, bool kFold = false>
 static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   using Lay = SmemLayout<kPair, kStages>;
-  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain>;
+  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain, kFold>;
   static bool configured = false;
   if (!configured) {
     NWX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
@@ -617,14 +665,16 @@ static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   return NWX_OK;
 }
 
-// variant: 0/1 = CTA pair + resident weights (production), 2 = CTA pair streaming,
-//          3 = single CTA streaming (cta_group::1)
+// variant: 0/1 = CTA pair + resident weights + folded feature layer (production), 2 = CTA pair streaming,
+//          3 = single CTA streaming (cta_group::1), 4 = as 1 with the reference's layer structure (no fold)
 int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st) {
   if (args.P <= 0) return NWX_OK;
   const bool tap = args.dbg_out != nullptr;
   switch (variant) {
     case 0:
-    case 1: return tap ? launch_variant<true, true, 4, true>(net, args, st) : launch_variant<true, true, 4, false>(net, args, st);
+    case 1: return tap ? launch_variant<true, true, 4, true, false, true>(net, args, st)
+                       : launch_variant<true, true, 4, false, false, true>(net, args, st);
+    case 4: return tap ? launch_variant<true, true, 4, true>(net, args, st) : launch_variant<true, true, 4, false>(net, args, st);
     case 2: return tap ? launch_variant<true, false, 4, true>(net, args, st) : launch_variant<true, false, 4, false>(net, args, st);
     case 3: return tap ? launch_variant<false, false, 2, true>(net, args, st) : launch_variant<false, false, 2, false>(net, args, st);
     default: return NWX_E_INVALID;

@@ -17,7 +17,10 @@ __host__ __device__ constexpr int layer_kblocks(int l) { return l == 0 ? 1 : (l 
 constexpr int kNumKBlocks = 1 + 4 * 4 + 5 + 4 * 4;           // 38
 constexpr int kFullKBlocks = kNumKBlocks - 4;                // 34 with N = 256, then 4 with N = 128
 constexpr int kKBlockBytes = 256 * 64 * 2;                   // one [256 x 64] bf16 image
-constexpr size_t kWeightImageBytes = (size_t)kFullKBlocks * kKBlockBytes + 4 * (kKBlockBytes / 2);
+// Inference folds _feature_linear into the views layer (no non-linearity between them, nerf_model.py:64-68):
+// W_fold = W_view[:, :256] . W_feature (128 x 256), kept as 4 more half-size K-blocks after the plain image.
+constexpr int kFoldKBlock0 = kNumKBlocks;                    // global K-block index of the folded views layer
+constexpr size_t kWeightImageBytes = (size_t)kFullKBlocks * kKBlockBytes + 8 * (kKBlockBytes / 2);
 
 __host__ __device__ constexpr uint32_t kblock_offset(int g) {
   return g < kFullKBlocks ? (uint32_t)g * kKBlockBytes
@@ -55,6 +58,7 @@ struct PackedNet {
   uint8_t* wimg = nullptr;           // device: swizzled bf16 K-block images (kWeightImageBytes)
   float* wdir_t = nullptr;           // device: [27][128] fp32 = _views_linears.0.weight[:, 256:]^T
   float* bview = nullptr;            // device: [128] fp32 _views_linears.0.bias
+  float* bview_fold = nullptr;       // device: [128] fp32 b_view + W_view[:, :256] . b_feature (folded inference path)
   MlpConsts consts;                  // host copy
   MlpConsts* gconsts = nullptr;      // device copy (training kernels read it through a pointer)
   uint8_t* wimg_t = nullptr;         // device: transposed-weight K-block images for the dX kernel
@@ -81,9 +85,10 @@ struct MlpArgs {
 };
 
 int pack_network(PackedNet& net, const float* const* tensors, cudaStream_t st);
-int pack_network_images(PackedNet& net, const float* const* tensors, cudaStream_t st);
-int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, float* out,
-                   cudaStream_t st);
+int pack_network_images(PackedNet& net, const float* const* tensors, bool with_fold, cudaStream_t st);
+inline bool variant_folds(int variant) { return variant <= 1; }
+int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, bool fold,
+                   float* out, cudaStream_t st);
 int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st);
 int launch_mlp_train_forward(const PackedNet& net, MlpArgs args, cudaStream_t st);
 

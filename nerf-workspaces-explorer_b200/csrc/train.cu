@@ -685,7 +685,7 @@ int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st) {
   if (!net.gconsts) NWX_CUDA_TRY(cudaMalloc(&net.gconsts, sizeof(MlpConsts)));
   TensorTable tab;
   for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) tab.t[i] = params_flat + g_flat.off[i];
-  int rc = pack_network_images(net, tab.t, st);
+  int rc = pack_network_images(net, tab.t, false, st);     // training keeps the reference's layer structure
   if (rc) return rc;
   PackTSrc ts;
   ts.w[0] = tab.t[16];

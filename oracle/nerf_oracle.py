@@ -188,8 +188,8 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def mlp_forward_bf16_emul(sd: Dict[str, torch.Tensor], pe_xyz: torch.Tensor, pe_dir: torch.Tensor
-                          ) -> torch.Tensor:
+def mlp_forward_bf16_emul(sd: Dict[str, torch.Tensor], pe_xyz: torch.Tensor, pe_dir: torch.Tensor,
+                          fold_feature: bool = True) -> torch.Tensor:
     """Numerics model of the CUDA engine's fused MLP (NOT reference behaviour).
 
     Same graph as :func:`mlp_forward`, with operands rounded to bf16 exactly where the
@@ -197,6 +197,12 @@ def mlp_forward_bf16_emul(sd: Dict[str, torch.Tensor], pe_xyz: torch.Tensor, pe_
     and every hidden activation fed to a tensor-core layer are bf16; accumulation, biases,
     the 27-d view-direction contribution, the sigma head and the rgb head stay fp32.
     Used by tests to check the kernel far tighter than the 1e-3 reference tolerance.
+
+    fold_feature=True models the production inference kernel, which folds ``_feature_linear`` into the
+    views layer at load time (no non-linearity between them, nerf_model.py:64-68): one 128x256 bf16
+    weight ``W_view[:, :256] @ W_feature`` (fp64 product, rounded once) applied to bf16 h8, its bias
+    ``b_view + W_view[:, :256] @ b_feature`` joining the per-ray fp32 term.  fold_feature=False models
+    the kernels that keep the reference's layer structure (training forward, MLP variants 2-4).
     """
     lin = torch.nn.functional.linear
     W = lambda k: _bf16(sd[k])
@@ -209,10 +215,16 @@ def mlp_forward_bf16_emul(sd: Dict[str, torch.Tensor], pe_xyz: torch.Tensor, pe_
         if i == 4:
             h = torch.cat([pts, h], -1)
     alpha = lin(h32, sd["_alpha_linear.weight"], sd["_alpha_linear.bias"])        # fp32 head on fp32 h7
-    feat = _bf16(lin(h, W("_feature_linear.weight")) + sd["_feature_linear.bias"])
     wv = sd["_views_linears.0.weight"]
-    dir_bias = lin(pe_dir, wv[:, 256:], sd["_views_linears.0.bias"])             # fp32, per ray
-    hv = torch.relu(lin(feat, _bf16(wv[:, :256])) + dir_bias)
+    if fold_feature:
+        w_fold = (wv[:, :256].double() @ sd["_feature_linear.weight"].double()).float()
+        b_fold = (sd["_views_linears.0.bias"].double()
+                  + wv[:, :256].double() @ sd["_feature_linear.bias"].double()).float()
+        hv = torch.relu(lin(h, _bf16(w_fold)) + lin(pe_dir, wv[:, 256:], b_fold))
+    else:
+        feat = _bf16(lin(h, W("_feature_linear.weight")) + sd["_feature_linear.bias"])
+        dir_bias = lin(pe_dir, wv[:, 256:], sd["_views_linears.0.bias"])         # fp32, per ray
+        hv = torch.relu(lin(feat, _bf16(wv[:, :256])) + dir_bias)
     rgb = lin(hv, sd["_rgb_linear.weight"], sd["_rgb_linear.bias"])
     return torch.cat([rgb, alpha], -1)
 

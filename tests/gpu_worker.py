@@ -34,7 +34,7 @@ def mlp_case(variant: int, n_points: int, tap_layer: int = -1) -> dict:
     dirs = torch.nn.functional.normalize(torch.randn(n_points, 3, generator=g), dim=-1)
     pe3, pe2 = orc.positional_encoding(pts, 10, 10), orc.positional_encoding(dirs, 4, 1)
     ref = orc.mlp_forward(sd, torch.cat([pe3, pe2], -1))
-    emu = orc.mlp_forward_bf16_emul(sd, pe3, pe2)
+    emu = orc.mlp_forward_bf16_emul(sd, pe3, pe2, fold_feature=variant <= 1)    # variants 2-4 keep the feature layer
     out = {"variant": variant, "n": n_points}
     tap = None
     if tap_layer >= 0:

@@ -53,6 +53,16 @@ def test_embedding_and_mlp():
     emul = orc.mlp_forward_bf16_emul(orc.init_state_dict(g["seed"]), pe3, pe2)
     assert float((emul - raw).abs().max()) < 2e-2        # bf16 operands vs fp32: small, not zero
     assert float((emul - raw).abs().max()) > 0
+    # the folded views layer (production inference kernel) is the same function: no further from the
+    # reference's fp32 output than the layer-by-layer bf16 model is
+    unfolded = orc.mlp_forward_bf16_emul(orc.init_state_dict(g["seed"]), pe3, pe2, fold_feature=False)
+    assert float((emul - raw).abs().max()) <= 1.25 * float((unfolded - raw).abs().max())
+    assert float((emul - unfolded).abs().max()) < 1e-3
+    sd = orc.init_state_dict(7, trained_like=True)
+    ref = orc.mlp_forward(sd, torch.cat([pe3, pe2], -1))
+    e_fold = float((orc.mlp_forward_bf16_emul(sd, pe3, pe2) - ref).abs().max())
+    e_plain = float((orc.mlp_forward_bf16_emul(sd, pe3, pe2, fold_feature=False) - ref).abs().max())
+    assert e_fold <= 1.25 * e_plain, (e_fold, e_plain)
 
 
 def test_raw2outputs():

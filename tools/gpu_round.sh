@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 OUT=gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit,memory.total --format=csv > $OUT/gpu.txt 2>&1
 nproc >> $OUT/gpu.txt; lscpu | grep -i "model name" >> $OUT/gpu.txt
-for v in 3 2 1; do
+for v in 4 3 2 1; do
   timeout 400 python tests/gpu_worker.py mlp $v 1000 0 > $OUT/worker_v$v.log 2>&1
   echo "worker variant $v rc=$?" | tee -a $OUT/summary.txt
   grep RESULT $OUT/worker_v$v.log | tee -a $OUT/summary.txt
