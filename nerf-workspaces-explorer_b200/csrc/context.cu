@@ -30,6 +30,7 @@ struct nwx_ctx {
   uint8_t* tscratch = nullptr;
   size_t tscratch_bytes = 0;
   float* partial = nullptr;      // [n_partials][NWX_PARAMS_PER_NET], zero-initialised once
+  double* loss_scratch = nullptr;   // ticket + per-block partial sums of the MSE kernel, zero-initialised once
   int n_partials = 0;
   bool profiling = false;
   bool ev_recorded = false;
@@ -125,6 +126,7 @@ extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->tscratch) cudaFree(ctx->tscratch);
   if (ctx->partial) cudaFree(ctx->partial);
+  if (ctx->loss_scratch) cudaFree(ctx->loss_scratch);
   for (auto& n : ctx->net) {
     if (n.wimg_t) cudaFree(n.wimg_t);
     if (n.gconsts) cudaFree(n.gconsts);
@@ -313,7 +315,7 @@ extern "C" int nwx_adam_step(float* params, const float* grads, float* m, float*
 
 namespace {
 struct TrainPlan {
-  size_t acts_c, acts_f, gimg, hv_c, hv_f, d_raw_c, d_raw_f, pe_dir, d_rgb_c, d_rgb_f, rgb_c, rgb_f, total;
+  size_t acts_c, acts_f, masks_c, masks_f, gimg, head_partial, hv_c, hv_f, d_raw_c, d_raw_f, pe_dir, d_rgb_c, d_rgb_f, rgb_c, rgb_f, total;
 };
 TrainPlan plan_train(int64_t N, int Sc, int Ni) {
   TrainPlan p{};
@@ -323,7 +325,10 @@ TrainPlan plan_train(int64_t N, int Sc, int Ni) {
   const int64_t tc = (N * Sc + 127) / 128, tf = (N * Sf + 127) / 128;
   p.acts_c = take(nwx::act_image_bytes(tc));
   p.acts_f = take(nwx::act_image_bytes(tf));
+  p.masks_c = take(nwx::mask_image_bytes(tc));
+  p.masks_f = take(nwx::mask_image_bytes(tf));
   p.gimg = take(nwx::grad_image_bytes(tf));            // reused: coarse backward, then fine backward
+  p.head_partial = take(nwx::head_partial_bytes(tf));  // reused like gimg
   p.hv_c = take((size_t)N * Sc * nwx::kViewHidden * 4);
   p.hv_f = take((size_t)N * Sf * nwx::kViewHidden * 4);
   p.d_raw_c = take((size_t)N * Sc * 16);
@@ -357,10 +362,14 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     ctx->tscratch_bytes = tp.total;
   }
   if (!ctx->partial) {
-    ctx->n_partials = nwx::num_sms();
+    ctx->n_partials = nwx::dw_partial_rows();
     const size_t bytes = (size_t)ctx->n_partials * NWX_PARAMS_PER_NET * sizeof(float);
     NWX_CUDA_TRY(cudaMalloc(&ctx->partial, bytes));
     NWX_CUDA_TRY(cudaMemsetAsync(ctx->partial, 0, bytes, st));
+  }
+  if (!ctx->loss_scratch) {
+    NWX_CUDA_TRY(cudaMalloc(&ctx->loss_scratch, nwx::kMseScratchBytes));
+    NWX_CUDA_TRY(cudaMemsetAsync(ctx->loss_scratch, 0, nwx::kMseScratchBytes, st));
   }
   float* s = ctx->scratch;
   uint8_t* ts = ctx->tscratch;
@@ -372,6 +381,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
   float* d_raw[2] = {reinterpret_cast<float*>(ts + tp.d_raw_c), reinterpret_cast<float*>(ts + tp.d_raw_f)};
   float* d_rgb[2] = {reinterpret_cast<float*>(ts + tp.d_rgb_c), reinterpret_cast<float*>(ts + tp.d_rgb_f)};
   uint8_t* acts[2] = {ts + tp.acts_c, ts + tp.acts_f};
+  uint32_t* masks[2] = {reinterpret_cast<uint32_t*>(ts + tp.masks_c), reinterpret_cast<uint32_t*>(ts + tp.masks_f)};
   float* pe_dir = reinterpret_cast<float*>(ts + tp.pe_dir);
 
   // ---- forward (training handler:534-618), operands saved for the backward ----
@@ -386,7 +396,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     nwx::MlpArgs a{};
     a.which = which;
     a.rays = io->rays; a.z = z; a.wimg = net.wimg; a.dirbias = dirb; a.raw_out = raw; a.diag = ctx->diag;
-    a.acts = acts[which]; a.hv_out = hv[which]; a.P = N * S; a.ray_dim = rd; a.S = S;
+    a.acts = acts[which]; a.masks = masks[which]; a.hv_out = hv[which]; a.P = N * S; a.ray_dim = rd; a.S = S;
     return nwx::launch_mlp_train_forward(net, a, st);
   };
   const nwx::RngSpec rj = rng_for(o, 0, o->t_rand, o->rng_jitter != 0), ru = rng_for(o, 1, o->u, o->rng_u != 0);
@@ -401,7 +411,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
   if ((rc = nwx::launch_composite_fwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, rnf, N, Sf, o->white_bkgd, rgb_f,
                                       nullptr, nullptr, nullptr, nullptr, nullptr, st))) return rc;
   // ---- loss (training handler:291-305) and backward through compositing; z_samples is detached (:580) ----
-  if ((rc = nwx::launch_mse_grad(rgb_c, rgb_f, io->gt_rgb, N, d_rgb[0], d_rgb[1], io->loss, st))) return rc;
+  if ((rc = nwx::launch_mse_grad(rgb_c, rgb_f, io->gt_rgb, N, d_rgb[0], d_rgb[1], ctx->loss_scratch, io->loss, st))) return rc;
   if ((rc = nwx::launch_composite_bwd(raw_c, z_c, io->rays + 3, rd, o->noise_coarse, rnc, d_rgb[0], N, Sc, o->white_bkgd,
                                       d_raw[0], st))) return rc;
   if ((rc = nwx::launch_composite_bwd(raw_f, z_f, io->rays + 3, rd, o->noise_fine, rnf, d_rgb[1], N, Sf, o->white_bkgd,
@@ -413,7 +423,8 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
   for (int w = 0; w < 2; ++w) {
     NWX_CUDA_TRY(cudaMemsetAsync(grads[w], 0, sizeof(float) * NWX_PARAMS_PER_NET, st));
     nwx::TrainBwdArgs b{};
-    b.d_raw = d_raw[w]; b.hv = hv[w]; b.acts = acts[w]; b.gimg = ts + tp.gimg; b.partial = ctx->partial;
+    b.d_raw = d_raw[w]; b.hv = hv[w]; b.acts = acts[w]; b.masks = masks[w]; b.gimg = ts + tp.gimg; b.partial = ctx->partial;
+    b.head_partial = reinterpret_cast<float*>(ts + tp.head_partial);
     b.pe_dir = pe_dir; b.grad = grads[w]; b.diag = ctx->diag; b.P = N * S[w]; b.S = S[w]; b.max_partials = ctx->n_partials;
     b.which = w;
     if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st))) return rc;

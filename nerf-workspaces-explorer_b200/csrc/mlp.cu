@@ -112,7 +112,8 @@ enum { kEpiRelu = 0, kEpiReluSigma = 1, kEpiLinear = 2 };
 // One 32-column chunk of the hidden-layer epilogue: +bias -> (ReLU) -> bf16 -> swizzled A tile.
 template <int kMode, bool kTap, bool kSave>
 __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, const uint32_t (&v)[32], int col, uint32_t hrow,
-                                               int row, float* tap_row, uint8_t* grow, float& sig) {
+                                               int row, float* tap_row, uint8_t* grow /* mask words of (tile, layer) */,
+                                               float& sig) {
   uint32_t pk[16];
   const bool no_sts = kTap && hrow == 0;          // timing experiment (debug instantiation only)
 #pragma unroll
@@ -138,12 +139,14 @@ __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, cons
   } else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) {
     st_shared_v4(kbase, pk[0], pk[5], pk[10], pk[15]);      // keeps the math alive
   }
-  if (kSave) {                                   // training: keep the same tile image in HBM for the backward
-    uint8_t* gk = grow + (size_t)(col >> 6) * kTileImgBytes;
+  if (kSave && kMode != kEpiLinear) {
+    // training: ReLU' of this row's 32 columns as one word for the dX kernel (bit j / 16 + j = low / high
+    // half of packed word j is non-zero), so the backward reads 4 B instead of 64 B of activations here.
+    // h >= +0 after the ReLU, so h + 0x7FFF carries into bit 15 exactly when h != 0.
+    uint32_t m = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<uint4*>(gk + (((j0 + q) ^ (row & 7)) << 4)) =
-          make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    for (int j = 0; j < 16; ++j) m |= ((pk[j] + 0x7FFF7FFFu) >> (15 - j)) & (0x00010001u << j);
+    reinterpret_cast<uint32_t*>(grow)[(col >> 5) * kTileM + row] = m;
   }
 }
 
@@ -400,13 +403,17 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           } else if (l < 9) {
             const uint32_t hrow = (kTap && args.dbg_layer == -3 && args.dbg_out != nullptr)
                                       ? 0u : sbase + L::h0 + t * kHBytes + row * 128;
+            uint8_t* mask_row = nullptr;         // training: ReLU' bit words of (tile, layer l), see mask_img_offset
+            if (kTrain && args.masks != nullptr && l < 8)
+              mask_row = reinterpret_cast<uint8_t*>(args.masks) +
+                         mask_img_offset(tile_of(it, t) < args.n_tiles ? tile_of(it, t) : args.n_tiles, l);
             if (l == 7) {
-              const float sig = epilogue_hidden<kEpiReluSigma, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
+              const float sig = epilogue_hidden<kEpiReluSigma, kTap, kTrain>(cst, l, d_tmem, hrow, row, wg, tap_row, mask_row);
               if (t == 0) sig0 = sig; else sig1 = sig;
             } else if (l == 8) {
               epilogue_hidden<kEpiLinear, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
             } else {
-              epilogue_hidden<kEpiRelu, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
+              epilogue_hidden<kEpiRelu, kTap, kTrain>(cst, l, d_tmem, hrow, row, wg, tap_row, mask_row);
             }
             fence_proxy_async_smem();            // my smem writes -> visible to the next layer's UMMA / TMA store
           } else {

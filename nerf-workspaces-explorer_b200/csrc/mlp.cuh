@@ -54,6 +54,12 @@ __host__ __device__ inline size_t tile_img_offset(int kb0, int nkb, int64_t n_ti
   return ((size_t)kb0 * n_tiles + (size_t)tile * nkb + kb) * kTileImgBytes;
 }
 
+// ReLU' bit masks for the dX kernel: per tile, per pts layer l = 0..7 (the layer that produced h_{l+1}), per
+// 32-column chunk c = 0..7, one uint32 per row: [tile][l][c][128 rows]; 32 KB per tile (256 B per point instead
+// of re-reading the 4 KB of activations).  One extra tile at the end takes the writes of tail tiles.
+constexpr size_t kMaskTileBytes = 8 * 8 * 128 * 4;
+__host__ __device__ inline size_t mask_img_offset(int64_t tile, int l) { return (size_t)tile * kMaskTileBytes + (size_t)l * 4096; }
+
 struct PackedNet {
   uint8_t* wimg = nullptr;           // device: swizzled bf16 K-block images (kWeightImageBytes)
   float* wdir_t = nullptr;           // device: [27][128] fp32 = _views_linears.0.weight[:, 256:]^T
@@ -79,6 +85,7 @@ struct MlpArgs {
   const MlpConsts* gconsts;          // training: biases / heads read from device memory
   uint8_t* acts;                     // training: activation tile images (see act slots), or nullptr
   float* hv_out;                     // training: views-layer hidden [P,128] fp32 (post-ReLU), or nullptr
+  uint32_t* masks;                   // training: ReLU' bit masks (mask_img_offset), or nullptr
   int64_t P;                         // total points
   int64_t n_tiles;                   // ceil(P / 128)
   int ray_dim, S, iters, dbg_layer, which;
@@ -97,8 +104,10 @@ struct TrainBwdArgs {
   const float* d_raw;        // [P,4]
   const float* hv;           // [P,128]
   const uint8_t* acts;       // activation images of this network's forward
+  const uint32_t* masks;     // ReLU' bit masks of this network's forward (mask_image_bytes)
   uint8_t* gimg;             // gradient image scratch (grad_image_bytes)
   float* partial;            // [max_partials][NWX_PARAMS_PER_NET] dW partials (zero-initialised once)
+  float* head_partial;       // head_partial_bytes(n_tiles): per-block sums of the head gradients
   const float* pe_dir;       // [n_rays,27] embedded view directions
   float* grad;               // flat gradient buffer of this network (accumulated into)
   uint32_t* diag;
@@ -109,11 +118,16 @@ int upload_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);  
 int upload_fwd_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);   // training forward (mlp.cu)
 size_t act_image_bytes(int64_t n_tiles);
 size_t grad_image_bytes(int64_t n_tiles);
+size_t head_partial_bytes(int64_t n_tiles);
+int dw_partial_rows();
+inline size_t mask_image_bytes(int64_t n_tiles) { return (size_t)(n_tiles + 1) * kMaskTileBytes; }
 const int* flat_offsets();
 int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st);
 int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st);
+constexpr int kMseMaxBlocks = 512;
+constexpr size_t kMseScratchBytes = (1 + 2 * kMseMaxBlocks) * sizeof(double);   // ticket word + per-block partial sums
 int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int64_t n_rays, float* d_c, float* d_f,
-                    double* loss_out, cudaStream_t st);
+                    double* loss_scratch, double* loss_out, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 int step, float grad_scale, cudaStream_t st);
 

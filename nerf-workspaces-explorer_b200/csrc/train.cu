@@ -86,6 +86,7 @@ struct DxArgs {
   const float* d_raw;        // [P,4] dL/d(raw rgb, raw sigma)
   const float* hv;           // [P,128] views hidden (post-ReLU) saved by the forward
   const uint8_t* acts;       // activation images (forward)
+  const uint32_t* masks;     // ReLU' bit masks (forward)
   uint8_t* grads;            // gradient images (output)
   const uint8_t* wimg_t;     // transposed weight images
   const MlpConsts* gconsts;
@@ -98,17 +99,18 @@ enum { kBwdLinear = 0, kBwdSigmaMask = 1, kBwdMask = 2 };
 
 template <int kKind>
 __device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tmem, uint32_t hrow, bool to_smem, bool to_gmem,
-                                             int row, int wg, const uint8_t* mrow, uint8_t* grow, float dsig) {
+                                             int row, int wg, const uint32_t* mrow, uint8_t* grow, float dsig) {
+  uint32_t mask[4] = {0u, 0u, 0u, 0u};                // ReLU' of this row's four 32-column chunks (forward's bit words)
+  if (kKind != kBwdLinear) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) mask[cc] = __ldg(mrow + (wg * 4 + cc) * kTileM);
+  }
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
     const int col = wg * 128 + cc * 32;
     const uint32_t kbo = (uint32_t)(col >> 6) * kTileImgBytes;
     const int j0 = (col & 63) >> 3;
-    uint4 m[4];
-    if (kKind != kBwdLinear) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) m[q] = __ldg(reinterpret_cast<const uint4*>(mrow + kbo + (((j0 + q) ^ (row & 7)) << 4)));
-    }
+    const uint32_t m = mask[cc];
     uint32_t v[32];
     tmem_ld32(d_tmem + col, v);
     tmem_wait_ld();
@@ -121,9 +123,8 @@ __device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tm
         b = fmaf(dsig, cst.w_alpha[col + j + 1], b);
       }
       if (kKind != kBwdLinear) {                    // ReLU': the saved activation is > 0
-        const uint32_t mw = (&m[j >> 3].x)[(j & 7) >> 1];
-        a = (mw & 0xFFFFu) ? a : 0.0f;
-        b = (mw >> 16) ? b : 0.0f;
+        a = (m & (1u << (j >> 1))) ? a : 0.0f;
+        b = (m & (0x10000u << (j >> 1))) ? b : 0.0f;
       }
       pk[j >> 1] = pack_bf16x2(a, b);
     }
@@ -306,7 +307,8 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           uint8_t* grow = args.grads + tile_img_offset(grad_slot_kb0(s + 1), 4, args.n_tiles + 1, wt, 0) + row * 128;
           // mask = activation that the produced gradient flows into: step 1 -> h8 (act slot 8) ... step 8 -> h1
           const int64_t mt = tile < args.n_tiles ? tile : 0;
-          const uint8_t* mrow = args.acts + tile_img_offset(act_slot_kb0(s == 0 ? 9 : 9 - s), 4, args.n_tiles, mt, 0) + row * 128;
+          const uint32_t* mrow = reinterpret_cast<const uint32_t*>(
+                                     reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(mt, s == 0 ? 0 : 8 - s)) + row;
           // Steps 0..6 leave their G tile in smem (next step's A operand) and save it with ONE TMA
           // store; steps 7 and 8 store per thread: after step 8's MMA the G_views producers reuse the
           // buffer, and they cannot wait on another thread's bulk group.
@@ -326,12 +328,13 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
               bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 1), 4, args.n_tiles + 1, wt, 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
           }
-          // the next step's ReLU mask (this row's two 128 B lines of the saved activation image):
-          // pull it into L2 now, one MMA step ahead, so the epilogue's loads do not wait on DRAM
-          if (s + 1 < kDxSteps && tile < args.n_tiles) {
-            const uint8_t* nm = args.acts + tile_img_offset(act_slot_kb0(8 - s), 4, args.n_tiles, tile, wg * 2) + row * 128;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nm));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + kTileImgBytes));
+          // the next step's ReLU' bit words (four 128 B lines per warp): pull them into L2 now, one MMA
+          // step ahead, so the epilogue's loads do not wait on DRAM
+          if (s + 1 < kDxSteps && tile < args.n_tiles && lane == 0) {
+            const uint8_t* nm = reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(tile, 7 - s) +
+                                (size_t)(wg * 4) * 512 + quad * 128;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + cc * 512));
           }
         }
       }
@@ -346,17 +349,21 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
 // ------------------------------------------------------------------------------------------------
 // dW kernel
 // ------------------------------------------------------------------------------------------------
+// Job-major: every CTA works on ONE (G, X) pair for its whole life -- a share of the tiles, one dW in TMEM, one
+// flush at the end -- instead of walking all 11 jobs with a TMEM flush (and an idle tensor pipe) between them.
 constexpr int kDwJobs = 11;
+constexpr int kDwMaxParts = 16;    // most CTAs one job is split over
 struct DwJob {
   int g_kb0, g_nkb;          // gradient image slot (K-block offset, count): out features = 64 * g_nkb
   int x_kb0, x_nkb;          // activation image slot: in features = 64 * x_nkb (n_valid of them real)
   int w_off, in_stride, col0, n_valid;   // where dW[out][col0 + c] goes in the flat gradient buffer
   int b_off;                 // bias gradient offset, or -1 (second job on the same G)
+  int cta0, ncta;            // the CTAs [cta0, cta0 + ncta) share this job: CTA cta0 + k takes tiles k, k + ncta, ...
 };
 struct DwArgs {
   const uint8_t* acts;
   const uint8_t* grads;
-  float* partial;            // [gridDim.x][NWX_PARAMS_PER_NET]
+  float* partial;            // [kDwMaxParts][NWX_PARAMS_PER_NET]: row k = the k-th CTA of each job
   uint32_t* diag;
   int64_t n_tiles;
   DwJob job[kDwJobs];
@@ -393,8 +400,11 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = args.n_tiles;
-  // my tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
-  const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  int jidx = 0;
+  while (jidx + 1 < kDwJobs && (int)blockIdx.x >= args.job[jidx].cta0 + args.job[jidx].ncta) ++jidx;
+  const DwJob jb = args.job[jidx];
+  const int part = (int)blockIdx.x - jb.cta0;      // my tiles: part, part + ncta, ...
+  const int my_tiles = (int)((n_tiles - part + jb.ncta - 1) / jb.ncta);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kDwStages; ++s) {
@@ -402,7 +412,6 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
       mbar_init(sbase + S::empty + 8 * s, 2);        // MMA commit + bias reducers
     }
     mbar_init(sbase + S::acc_full, 1);
-    mbar_init(sbase + S::acc_free, 4);               // one per flush warp
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<1>(sbase + S::tmem_slot, 512);
@@ -410,17 +419,16 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + S::tmem_slot);
-  float* partial = args.partial + (size_t)blockIdx.x * NWX_PARAMS_PER_NET;
+  float* partial = args.partial + (size_t)part * NWX_PARAMS_PER_NET;
 
   if (warp == 0) {
     if (lane == 0) {                                           // ---- producer: 64-point half tiles of G and X
       const WaitCtx wc{args.diag, 0x2100u};
       uint32_t fill = 0;
-      for (int j = 0; j < kDwJobs; ++j) {
-        const DwJob jb = args.job[j];
+      {
         const uint32_t bytes = (uint32_t)(jb.g_nkb + jb.x_nkb) * 8192u;
         for (int i = 0; i < my_tiles; ++i) {
-          const int64_t tile = blockIdx.x + (int64_t)i * gridDim.x;
+          const int64_t tile = part + (int64_t)i * jb.ncta;
           for (int half = 0; half < 2; ++half, ++fill) {
             const uint32_t stage = fill % kDwStages, round = fill / kDwStages;
             mbar_wait(sbase + S::empty + 8 * stage, (round & 1) ^ 1, wc);
@@ -441,12 +449,9 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
     if (lane == 0) {                                           // ---- MMA issuer
       const WaitCtx wc{args.diag, 0x2200u};
       uint32_t fill = 0;
-      for (int j = 0; j < kDwJobs; ++j) {
-        const DwJob jb = args.job[j];
+      {
         const int mhalves = jb.g_nkb / 2;
         const uint32_t idesc = umma_idesc_bf16_mn(128, 64 * jb.x_nkb);
-        if (j > 0) mbar_wait(sbase + S::acc_free, (j - 1) & 1, wc);      // previous dW flushed out of TMEM
-        tc_fence_after();
         for (int i = 0; i < 2 * my_tiles; ++i, ++fill) {
           const uint32_t stage = fill % kDwStages, round = fill / kDwStages;
           mbar_wait(sbase + S::full + 8 * stage, round & 1, wc);
@@ -470,9 +475,8 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
     const WaitCtx wc{args.diag, 0x2300u};
     const int quad = warp & 3;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int j = 0; j < kDwJobs; ++j) {
-      const DwJob jb = args.job[j];
-      mbar_wait(sbase + S::acc_full, j & 1, wc);
+    {
+      mbar_wait(sbase + S::acc_full, 0, wc);
       tc_fence_after();
       for (int mh = 0; mh < jb.g_nkb / 2; ++mh) {
         const int o = mh * 128 + quad * 32 + lane;
@@ -486,17 +490,13 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
             if (c0 + c < jb.n_valid) dst[c0 + c] = __uint_as_float(v[c]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sbase + S::acc_free);
     }
   } else if (warp >= 8) {
     // ---- bias gradients: column sums of the G half-tiles, straight from shared memory
     const WaitCtx wc{args.diag, 0x2400u};
     const int c = threadIdx.x - 256;                 // column 0..255
     uint32_t fill = 0;
-    for (int j = 0; j < kDwJobs; ++j) {
-      const DwJob jb = args.job[j];
+    {
       const bool mine = jb.b_off >= 0 && c < 64 * jb.g_nkb;
       float acc = 0.f;
       for (int i = 0; i < 2 * my_tiles; ++i, ++fill) {
@@ -520,11 +520,24 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// grad[i] += sum over CTAs of partial[cta][i]
+// grad[i] += sum over the CTAs of the job that owns parameter i of partial[k][i], k < that job's ncta
+struct DwJobTable { DwJob job[kDwJobs]; };
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ partial, int n_parts, float* __restrict__ grad) {
+reduce_partials_kernel(const float* __restrict__ partial, const __grid_constant__ DwJobTable tab, float* __restrict__ grad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NWX_PARAMS_PER_NET) return;
+  int n_parts = 0;                                   // 0: not produced by the dW kernel (heads, view-direction columns)
+#pragma unroll 1
+  for (int j = 0; j < kDwJobs; ++j) {
+    const DwJob& jb = tab.job[j];
+    const int rows = 64 * jb.g_nkb;
+    if (i >= jb.w_off && i < jb.w_off + rows * jb.in_stride) {
+      const int col = (i - jb.w_off) % jb.in_stride;
+      if (col >= jb.col0 && col < jb.col0 + jb.n_valid) { n_parts = jb.ncta; break; }
+    }
+    if (jb.b_off >= 0 && i >= jb.b_off && i < jb.b_off + rows) { n_parts = jb.ncta; break; }
+  }
+  if (n_parts == 0) return;
   float s = 0.f;
   for (int c = 0; c < n_parts; ++c) s += partial[(size_t)c * NWX_PARAMS_PER_NET + i];
   grad[i] += s;
@@ -540,19 +553,22 @@ struct HeadArgs {
   const uint8_t* acts;       // h8 images (act slot 8)
   const float* pe_dir;       // [n_rays, 27]
   const MlpConsts* gconsts;
-  float* grad;               // flat gradient buffer of the net (atomics)
+  float* head_partial;       // [gridDim.x][kHeadOut] per-block sums (no atomics: deterministic)
   int64_t P, n_tiles;
   int S;
-  int off_wv, off_walpha, off_balpha, off_wrgb, off_brgb;
 };
+// per-block output layout: w_rgb [3][128] | view-direction columns [128][27] | w_alpha [256] | b_rgb [3], b_alpha
+constexpr int kHeadOffDir = 3 * kViewHidden, kHeadOffAlpha = kHeadOffDir + kViewHidden * kPeDir,
+              kHeadOffBias = kHeadOffAlpha + kHidden, kHeadValid = kHeadOffBias + 4, kHeadOut = 4128;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 head_grads_kernel(const HeadArgs a) {
   // threads 0..127: one views-hidden column each (rgb head, view-direction columns of the views
   // layer); threads 128..255: two h8 columns each (sigma head).  A block owns kHeadTiles
-  // consecutive tiles, accumulates in registers and finishes with one atomicAdd per output.
+  // consecutive tiles, accumulates in registers and writes its sums to its own row of head_partial.
   const int tid = threadIdx.x;
   const MlpConsts& cst = *a.gconsts;
+  __shared__ float4 sd[kTileM];                     // d_raw of the current tile
   float wr[3] = {0.f, 0.f, 0.f}, d_wr[3] = {0.f, 0.f, 0.f}, d_dir[kPeDir];
   float d_wa[2] = {0.f, 0.f}, d_b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -562,31 +578,33 @@ head_grads_kernel(const HeadArgs a) {
   for (int64_t tile = tile0; tile < tile0 + kHeadTiles && tile < a.n_tiles; ++tile) {
     const int64_t p0 = tile * kTileM;
     const int n = (int)((a.P - p0) < kTileM ? (a.P - p0) : kTileM);
+    __syncthreads();                                            // previous tile's readers are done with sd
+    if (tid < kTileM) sd[tid] = tid < n ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + p0 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
     if (tid < kViewHidden) {
       float gsum = 0.f;
       int64_t ray = p0 / a.S;
       int left = a.S - (int)(p0 - ray * a.S);                   // points left in the current ray (no per-point division)
       for (int r0 = 0; r0 < n; r0 += 8) {
-        float4 d[8];
         float h[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {                           // 8 points in flight: all loads first
           const int64_t p = p0 + ((r0 + q < n) ? r0 + q : n - 1);
-          d[q] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + p);
-          h[q] = __ldg(a.hv + p * kViewHidden + tid);
+          h[q] = ldg_stream(a.hv + p * kViewHidden + tid);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (r0 + q >= n) break;
+          const float4 dq = sd[r0 + q];
           if (left == 0) {                                      // ray boundary: fold the ray's sum of g_v
 #pragma unroll
             for (int i = 0; i < kPeDir; ++i) d_dir[i] = fmaf(gsum, __ldg(a.pe_dir + ray * kPeDir + i), d_dir[i]);
             gsum = 0.f; ++ray; left = a.S;
           }
           --left;
-          d_wr[0] = fmaf(d[q].x, h[q], d_wr[0]); d_wr[1] = fmaf(d[q].y, h[q], d_wr[1]); d_wr[2] = fmaf(d[q].z, h[q], d_wr[2]);
-          if (h[q] > 0.f) gsum += fmaf(wr[0], d[q].x, fmaf(wr[1], d[q].y, wr[2] * d[q].z));
-          if (tid == 0) { d_b[0] += d[q].x; d_b[1] += d[q].y; d_b[2] += d[q].z; d_b[3] += d[q].w; }
+          d_wr[0] = fmaf(dq.x, h[q], d_wr[0]); d_wr[1] = fmaf(dq.y, h[q], d_wr[1]); d_wr[2] = fmaf(dq.z, h[q], d_wr[2]);
+          if (h[q] > 0.f) gsum += fmaf(wr[0], dq.x, fmaf(wr[1], dq.y, wr[2] * dq.z));
+          if (tid == 0) { d_b[0] += dq.x; d_b[1] += dq.y; d_b[2] += dq.z; d_b[3] += dq.w; }
         }
       }
 #pragma unroll
@@ -596,43 +614,68 @@ head_grads_kernel(const HeadArgs a) {
       const uint8_t* img = a.acts + tile_img_offset(act_slot_kb0(8), 4, a.n_tiles, tile, c0 >> 6) + (c0 & 7) * 2;
       const int ch = (c0 & 63) >> 3;
       for (int r0 = 0; r0 < n; r0 += 8) {
-        float ds[8];
         uint32_t hh[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int r = (r0 + q < n) ? r0 + q : n - 1;
-          ds[q] = (r0 + q < n) ? __ldg(a.d_raw + (p0 + r) * 4 + 3) : 0.f;
           hh[q] = *reinterpret_cast<const uint32_t*>(img + r * 128 + ((ch ^ (r & 7)) << 4));
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          d_wa[0] = fmaf(ds[q], __uint_as_float(hh[q] << 16), d_wa[0]);
-          d_wa[1] = fmaf(ds[q], __uint_as_float(hh[q] & 0xFFFF0000u), d_wa[1]);
+          const float ds = sd[r0 + q].w;                        // zero past the end of the batch
+          d_wa[0] = fmaf(ds, __uint_as_float(hh[q] << 16), d_wa[0]);
+          d_wa[1] = fmaf(ds, __uint_as_float(hh[q] & 0xFFFF0000u), d_wa[1]);
         }
       }
     }
   }
+  float* hp = a.head_partial + (size_t)blockIdx.x * kHeadOut;
   if (tid < kViewHidden) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) atomicAdd(a.grad + a.off_wrgb + c * kViewHidden + tid, d_wr[c]);
+    for (int c = 0; c < 3; ++c) hp[c * kViewHidden + tid] = d_wr[c];
 #pragma unroll
-    for (int i = 0; i < kPeDir; ++i) atomicAdd(a.grad + a.off_wv + tid * (kHidden + kPeDir) + kHidden + i, d_dir[i]);
+    for (int i = 0; i < kPeDir; ++i) hp[kHeadOffDir + tid * kPeDir + i] = d_dir[i];
     if (tid == 0) {
-      for (int c = 0; c < 3; ++c) atomicAdd(a.grad + a.off_brgb + c, d_b[c]);
-      atomicAdd(a.grad + a.off_balpha, d_b[3]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) hp[kHeadOffBias + c] = d_b[c];
     }
   } else {
     const int c0 = (tid - kViewHidden) * 2;
-    atomicAdd(a.grad + a.off_walpha + c0, d_wa[0]);
-    atomicAdd(a.grad + a.off_walpha + c0 + 1, d_wa[1]);
+    hp[kHeadOffAlpha + c0] = d_wa[0];
+    hp[kHeadOffAlpha + c0 + 1] = d_wa[1];
   }
 }
 
+// grad[dst(i)] += sum over blocks of head_partial[block][i]; four independent chains per thread hide the load latency
+__global__ void __launch_bounds__(128)
+reduce_heads_kernel(const float* __restrict__ hp, int n_blocks, float* __restrict__ grad, int off_wv, int off_walpha,
+                    int off_balpha, int off_wrgb, int off_brgb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kHeadValid) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= n_blocks; b += 4) {
+    s0 += hp[(size_t)(b + 0) * kHeadOut + i]; s1 += hp[(size_t)(b + 1) * kHeadOut + i];
+    s2 += hp[(size_t)(b + 2) * kHeadOut + i]; s3 += hp[(size_t)(b + 3) * kHeadOut + i];
+  }
+  for (; b < n_blocks; ++b) s0 += hp[(size_t)b * kHeadOut + i];
+  int dst;
+  if (i < kHeadOffDir) dst = off_wrgb + i;
+  else if (i < kHeadOffAlpha) { const int k = i - kHeadOffDir; dst = off_wv + (k / kPeDir) * (kHidden + kPeDir) + kHidden + k % kPeDir; }
+  else if (i < kHeadOffBias) dst = off_walpha + (i - kHeadOffAlpha);
+  else dst = (i - kHeadOffBias < 3) ? off_brgb + (i - kHeadOffBias) : off_balpha;
+  grad[dst] += (s0 + s1) + (s2 + s3);
+}
+
 // d(loss)/d(rgb) for loss = mean((rgb_c - gt)^2) + mean((rgb_f - gt)^2)  (training handler:291-305);
-// loss_out[0..1] accumulate the two MSE terms (double, like the reference's fp64 loss).
+// loss_out[0..1] = the two MSE terms (double, like the reference's fp64 loss).  Summed in a fixed order
+// (thread -> warp -> block -> last block over the per-block partials), so two runs agree bit for bit.
 __global__ void __launch_bounds__(256)
 mse_grad_kernel(const float* __restrict__ rgb_c, const float* __restrict__ rgb_f, const float* __restrict__ gt,
-                int64_t n3, float* __restrict__ d_c, float* __restrict__ d_f, double* __restrict__ loss_out) {
+                int64_t n3, float* __restrict__ d_c, float* __restrict__ d_f, double* __restrict__ part,
+                unsigned int* __restrict__ ticket, double* __restrict__ loss_out) {
+  __shared__ double sw[8][2];
+  __shared__ bool last;
   double lc = 0.0, lf = 0.0;
   const float scale = 2.0f / (float)n3;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) {
@@ -642,7 +685,23 @@ mse_grad_kernel(const float* __restrict__ rgb_c, const float* __restrict__ rgb_f
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { lc += __shfl_xor_sync(kFull, lc, o); lf += __shfl_xor_sync(kFull, lf, o); }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(loss_out, lc / (double)n3); atomicAdd(loss_out + 1, lf / (double)n3); }
+  if ((threadIdx.x & 31) == 0) { sw[threadIdx.x >> 5][0] = lc; sw[threadIdx.x >> 5][1] = lf; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bc = 0.0, bf = 0.0;
+    for (int w = 0; w < 8; ++w) { bc += sw[w][0]; bf += sw[w][1]; }
+    part[2 * blockIdx.x] = bc; part[2 * blockIdx.x + 1] = bf;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double tc = 0.0, tf = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) { tc += __ldcg(part + 2 * b); tf += __ldcg(part + 2 * b + 1); }
+    loss_out[0] = tc / (double)n3; loss_out[1] = tf / (double)n3;
+    *ticket = 0u;                                               // ready for the next launch on this stream
+  }
 }
 
 // torch.optim.Adam, default betas/eps, no weight decay (training handler:234); g is pre-scaled by grad_scale.
@@ -702,6 +761,8 @@ int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st) {
 
 // ---- launchers ------------------------------------------------------------------------------------
 size_t act_image_bytes(int64_t n_tiles) { return (size_t)kActKBlocksPerTile * n_tiles * kTileImgBytes; }
+int dw_partial_rows() { return kDwMaxParts; }
+size_t head_partial_bytes(int64_t n_tiles) { return (size_t)((n_tiles + kHeadTiles - 1) / kHeadTiles) * kHeadOut * sizeof(float); }
 size_t grad_image_bytes(int64_t n_tiles) { return (size_t)kGradKBlocksPerTile * (n_tiles + 1) * kTileImgBytes; }
 
 // Backward of one network: d_raw [P,4] -> flat gradient buffer `grad` (state_dict order, += into it).
@@ -717,7 +778,7 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
       configured = true;
     }
     DxArgs d{};
-    d.d_raw = a.d_raw; d.hv = a.hv; d.acts = a.acts; d.grads = a.gimg; d.wimg_t = net.wimg_t; d.gconsts = net.gconsts;
+    d.d_raw = a.d_raw; d.hv = a.hv; d.acts = a.acts; d.masks = a.masks; d.grads = a.gimg; d.wimg_t = net.wimg_t; d.gconsts = net.gconsts;
     d.diag = a.diag; d.P = a.P; d.n_tiles = tiles; d.which = a.which;
     const int units = (num_sms() & ~1) / 2;
     int64_t need = (tiles + 3) / 4;
@@ -733,9 +794,7 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     g_nwx_launches.fetch_add(1, std::memory_order_relaxed);
   }
   // ---- dW ----
-  int grid = num_sms();
-  if (grid > tiles) grid = (int)tiles;
-  if (grid > a.max_partials) grid = a.max_partials;
+  int grid = 0;
   {
     static bool configured = false;
     if (!configured) {
@@ -747,7 +806,7 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     const int* off = g_flat.off;
     auto job = [&](int j, int gslot, int aslot, int wt, int stride, int col0, int nvalid, int bt) {
       w.job[j] = DwJob{grad_slot_kb0(gslot), grad_slot_nkb(gslot), act_slot_kb0(aslot), act_slot_nkb(aslot),
-                       off[wt], stride, col0, nvalid, bt >= 0 ? off[bt] : -1};
+                       off[wt], stride, col0, nvalid, bt >= 0 ? off[bt] : -1, 0, 0};
     };
     job(0, 9, 0, 0, 63, 0, 63, 1);                 // pts0: G1 x PE
     for (int l = 1; l <= 4; ++l) job(l, 9 - l, l, 2 * l, 256, 0, 256, 2 * l + 1);   // pts1..4: G_{l+1} x h_l
@@ -757,27 +816,58 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     job(8, 2, 7, 14, 256, 0, 256, 15);             // pts7: G8 x h7
     job(9, 1, 8, 18, 256, 0, 256, 19);             // feature: d_f x h8
     job(10, 0, 9, 16, 283, 0, 256, 17);            // views: G_v x f
+    // CTAs per job in proportion to the bytes a job streams per tile (largest remainder), at most
+    // kDwMaxParts and never more than there are tiles
+    int units = 0, given = 0, parts[kDwJobs];
+    for (int j = 0; j < kDwJobs; ++j) units += w.job[j].g_nkb + w.job[j].x_nkb;
+    const int sms = num_sms();
+    for (int j = 0; j < kDwJobs; ++j) {
+      parts[j] = sms * (w.job[j].g_nkb + w.job[j].x_nkb) / units;
+      if (parts[j] < 1) parts[j] = 1;
+      given += parts[j];
+    }
+    for (int left = sms - given; left > 0;) {        // hand the remainder to the jobs with the most work per CTA
+      int best = -1;
+      double worst = 0.0;
+      for (int j = 0; j < kDwJobs; ++j) {
+        const double load = (double)(w.job[j].g_nkb + w.job[j].x_nkb) / parts[j];
+        if (parts[j] < kDwMaxParts && load > worst) { worst = load; best = j; }
+      }
+      if (best < 0) break;
+      ++parts[best]; --left;
+    }
+    for (int j = 0; j < kDwJobs; ++j) {
+      int n = parts[j] > kDwMaxParts ? kDwMaxParts : parts[j];
+      if (n > tiles) n = (int)tiles;
+      w.job[j].cta0 = grid; w.job[j].ncta = n;
+      grid += n;
+    }
     mlp_bwd_dw_kernel<<<grid, 512, DwSmem::alloc_bytes, st>>>(w);
     NWX_LAUNCHED();
+    DwJobTable tab;
+    for (int j = 0; j < kDwJobs; ++j) tab.job[j] = w.job[j];
+    reduce_partials_kernel<<<(NWX_PARAMS_PER_NET + 255) / 256, 256, 0, st>>>(a.partial, tab, a.grad);
+    NWX_LAUNCHED();
   }
-  reduce_partials_kernel<<<(NWX_PARAMS_PER_NET + 255) / 256, 256, 0, st>>>(a.partial, grid, a.grad);
-  NWX_LAUNCHED();
   HeadArgs h{};
-  h.d_raw = a.d_raw; h.hv = a.hv; h.acts = a.acts; h.pe_dir = a.pe_dir; h.gconsts = net.gconsts; h.grad = a.grad;
-  h.P = a.P; h.n_tiles = tiles; h.S = a.S;
-  h.off_wv = g_flat.off[16]; h.off_walpha = g_flat.off[20]; h.off_balpha = g_flat.off[21];
-  h.off_wrgb = g_flat.off[22]; h.off_brgb = g_flat.off[23];
-  head_grads_kernel<<<(unsigned)((tiles + kHeadTiles - 1) / kHeadTiles), 256, 0, st>>>(h);
+  h.d_raw = a.d_raw; h.hv = a.hv; h.acts = a.acts; h.pe_dir = a.pe_dir; h.gconsts = net.gconsts;
+  h.head_partial = a.head_partial; h.P = a.P; h.n_tiles = tiles; h.S = a.S;
+  const int head_blocks = (int)((tiles + kHeadTiles - 1) / kHeadTiles);
+  head_grads_kernel<<<head_blocks, 256, 0, st>>>(h);
+  NWX_LAUNCHED();
+  reduce_heads_kernel<<<(kHeadValid + 127) / 128, 128, 0, st>>>(a.head_partial, head_blocks, a.grad, g_flat.off[16], g_flat.off[20],
+                                                               g_flat.off[21], g_flat.off[22], g_flat.off[23]);
   NWX_LAUNCHED();
   return NWX_OK;
 }
 
 int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int64_t n_rays, float* d_c, float* d_f,
-                    double* loss_out, cudaStream_t st) {
-  NWX_CUDA_TRY(cudaMemsetAsync(loss_out, 0, 2 * sizeof(double), st));
+                    double* loss_scratch, double* loss_out, cudaStream_t st) {
+  // loss_scratch: kMseScratchBytes, zero before the first use (the kernel leaves the ticket at zero)
   int64_t blocks = (n_rays * 3 + 255) / 256;
-  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-  mse_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(rgb_c, rgb_f, gt, n_rays * 3, d_c, d_f, loss_out);
+  if (blocks > kMseMaxBlocks) blocks = kMseMaxBlocks;
+  mse_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(rgb_c, rgb_f, gt, n_rays * 3, d_c, d_f, loss_scratch + 1,
+                                                    reinterpret_cast<unsigned int*>(loss_scratch), loss_out);
   NWX_LAUNCHED();
   return NWX_OK;
 }

@@ -204,6 +204,8 @@ class NeRFReplicaTrainingHandler:
                                white_bkgd=bool(rnd["white_background"]), perturb=float(rnd["perturb"]),
                                raw_noise_std=float(rnd["raw_noise_std"]), seed=seed)
         self._gen = torch.Generator(device=dev).manual_seed(seed)
+        self._chunk = number(cfg.get("model", {}).get("chunk", 1024 * 32))   # rays per render call (yaml model.chunk)
+        self._train_mode, self._weights_version = True, -1
 
     def _sample_training_data(self):
         """One random image, n_rays random pixels with replacement (training handler:341-370)."""
@@ -211,6 +213,46 @@ class NeRFReplicaTrainingHandler:
         img = int(torch.randint(0, num_img, (1,), device=self.rays_train.device, generator=self._gen))
         pix = torch.randint(0, num_ray, (self._n_rays,), device=self.rays_train.device, generator=self._gen)
         return self.rays_train[img, pix], self._train_rgbs[img, pix]
+
+    # ---- forward-only renders (eval renders of the reference's loop, training handler:479-532) ----
+    def set_train_mode(self, on: bool) -> None:
+        """training handler:110-116 toggles `_train_mode`: jitter / noise only while training."""
+        self._train_mode = bool(on)
+
+    @torch.no_grad()
+    def _volumetric_rendering(self, ray_batch: torch.Tensor, t_rand: Optional[torch.Tensor] = None,
+                              u: Optional[torch.Tensor] = None, noise_coarse: Optional[torch.Tensor] = None,
+                              noise_fine: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """training handler:534-618 -> the reference's 11-key dict with the CURRENT weights.  In train mode the
+        coarse depths are jittered (:547-565), u is random (:578) and sigma noise is added (raw_noise_std);
+        the draws come from the in-kernel generator unless tensors are injected (tests inject the
+        reference's own draws).  Forward only: gradients are produced by `step`."""
+        tr = self.trainer
+        if self._weights_version != tr.opt_steps:                 # host-side constants follow the optimiser
+            tr.sync_inference_weights()
+            self._weights_version = tr.opt_steps
+        train = getattr(self, "_train_mode", True)
+        rng = None
+        if train:
+            rng = _engine.RngOptions(tr.seed, tr.draws, jitter=tr.perturb > 0., random_u=tr.perturb > 0.,
+                                     noise_std=tr.raw_noise_std if tr.raw_noise_std > 0. else 0.0)
+            tr.draws += 1
+        out = self._engine.render_rays(ray_batch.to(self._engine.device), tr.n_samples, tr.n_importance, tr.white_bkgd,
+                                       want=_engine.REFERENCE_KEYS, t_rand=t_rand, u=u, noise_coarse=noise_coarse,
+                                       noise_fine=noise_fine, rng=rng)
+        self.last_flags = out.pop("flags")
+        return {k: out[k] for k in _engine.REFERENCE_KEYS}
+
+    def _render_rays(self, flat_rays: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """training handler:510-532: chunked render of [n,11] rays -> dict of [n, ...] tensors."""
+        from .batch_utils import batchify_rays
+        shape = flat_rays.shape
+        out = batchify_rays(self._volumetric_rendering, flat_rays.to(self._engine.device), self._chunk)
+        return {k: torch.reshape(v, list(shape[:-1]) + list(v.shape[1:])) for k, v in out.items()}
+
+    def save_checkpoint(self, path: str, global_step: int) -> None:
+        """training handler:394-409 (same dict layout, loadable by the reference's inference handler)."""
+        self.trainer.save_checkpoint(path, global_step)
 
     def step(self, global_step: int) -> Dict[str, torch.Tensor]:
         rays, gt = self._sample_training_data()

@@ -141,6 +141,39 @@ def test_training_handler_step():
     assert torch.isfinite(out["total_loss"]) and float(out["total_loss"]) > 0
 
 
+def test_training_handler_render_methods_vs_reference_golden():
+    """NeRFReplicaTrainingHandler._volumetric_rendering / _render_rays (training handler:510-618) with the
+    reference's own random draws injected: same 11 keys, same maps as the reference's golden output; after
+    an optimiser step the renders follow the new weights; eval mode renders deterministically."""
+    import nwx
+    g = load_golden("render_train")
+    sd_c, sd_f = _nets()
+    fx, fy, cx, cy = orc.intrinsics(24, 32)
+    bank = nwx.create_rays(2, orc.synthetic_poses(2, 1), 24, 32, fx, fy, cx, cy, 0.1, 10.0)
+    h = nwx.NeRFReplicaTrainingHandler("office_tokyo", None, bank, torch.rand(2, 24, 32, 3), sd_c, sd_f)
+    rays = g["rays"].to(DEV)
+    out = h._volumetric_rendering(rays, t_rand=g["t_rand"].to(DEV), u=g["u"].to(DEV),
+                                  noise_coarse=g["noise_c"].to(DEV), noise_fine=g["noise_f"].to(DEV))
+    assert tuple(out) == tuple(orc.REFERENCE_KEYS)
+    for k in ("rgb_coarse", "rgb_fine", "acc_coarse", "acc_fine"):
+        assert float((out[k].cpu() - g[k]).abs().max()) <= 1e-3, k                  # north_star tolerance
+    for k in ("depth_coarse", "depth_fine"):
+        assert float((out[k].cpu() - g[k]).abs().max()) <= 1e-3 * 9.9, k            # 1e-3 of the depth range
+    assert out["raw_fine"].shape == (rays.shape[0], 192, 4) and out["z_std"].shape == (rays.shape[0],)
+    h.set_train_mode(False)                                                          # eval renders: no jitter, no noise
+    a, b = h._render_rays(rays), h._render_rays(rays)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    h._chunk = 7                                                                     # ragged chunks give the same rays
+    c = h._render_rays(rays)
+    assert all(torch.equal(a[k], c[k]) for k in a)
+    h.set_train_mode(True)
+    h.step(0)                                                                        # weights move -> renders move
+    h.set_train_mode(False)
+    d = h._render_rays(rays)
+    assert not torch.equal(a["rgb_fine"], d["rgb_fine"])
+    assert float((a["rgb_fine"] - d["rgb_fine"]).abs().max()) < 0.05                 # one Adam step at lr 5e-4
+
+
 def test_checkpoint_round_trip_reference_format(tmp_path):
     """Trainer -> reference-format .ckpt -> (a) torch.optim.Adam accepts the optimizer state,
     (b) the inference handler loads it through initialize_models (handler:130-141) and renders with
