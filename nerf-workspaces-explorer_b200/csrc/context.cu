@@ -328,7 +328,7 @@ TrainPlan plan_train(int64_t N, int Sc, int Ni) {
   p.masks_c = take(nwx::mask_image_bytes(tc));
   p.masks_f = take(nwx::mask_image_bytes(tf));
   p.gimg = take(nwx::grad_image_bytes(tf));            // reused: coarse backward, then fine backward
-  p.head_partial = take(nwx::head_partial_bytes(tf));  // reused like gimg
+  p.head_partial = take(nwx::head_partial_bytes(tf, N, Sf));  // reused like gimg
   p.hv_c = take((size_t)N * Sc * nwx::kViewHidden * 4);
   p.hv_f = take((size_t)N * Sf * nwx::kViewHidden * 4);
   p.d_raw_c = take((size_t)N * Sc * 16);

@@ -118,7 +118,7 @@ int upload_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);  
 int upload_fwd_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);   // training forward (mlp.cu)
 size_t act_image_bytes(int64_t n_tiles);
 size_t grad_image_bytes(int64_t n_tiles);
-size_t head_partial_bytes(int64_t n_tiles);
+size_t head_partial_bytes(int64_t n_tiles, int64_t n_rays, int S);
 int dw_partial_rows();
 inline size_t mask_image_bytes(int64_t n_tiles) { return (size_t)(n_tiles + 1) * kMaskTileBytes; }
 const int* flat_offsets();

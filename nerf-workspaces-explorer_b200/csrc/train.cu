@@ -16,7 +16,7 @@
 //       transposes anywhere.  Each CTA accumulates a full dW in TMEM (2 x [128 x 256] fp32) over its
 //       share of the tiles and writes one partial; bias gradients are column sums of the G tiles
 //       taken from shared memory by otherwise idle warps.  A small kernel reduces the partials.
-//   head_grads_kernel: rgb / sigma heads and the 27 view-direction columns of the views layer (fp32).
+//   head_{rgb,dir,sigma}_kernel: rgb / sigma heads and the 27 view-direction columns of the views layer (fp32).
 #include "mlp_device.cuh"
 
 namespace nwx {
@@ -243,11 +243,21 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
         const bool live = p < P;
         float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) dr = __ldg(reinterpret_cast<const float4*>(args.d_raw) + p);
+        // this row of hv (512 B) was prefetched into L2 one tile ahead; fetch the next tile's row now, so the
+        // serialized chunk loop below runs at L2 latency while the tensor pipe waits for this tile
+        {
+          const int64_t pn = (t == 0 ? tile_of(it, 1) : tile_of(it + 1, 0)) * kTileM + row;
+          if (pn < P) {
+            const float* nx = args.hv + pn * kViewHidden;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + q * 32));
+          }
+        }
         if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
         const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
         uint8_t* grow = (tile < args.n_tiles)
                             ? args.grads + tile_img_offset(grad_slot_kb0(0), 2, args.n_tiles + 1, tile, 0) + row * 128 : nullptr;
-#pragma unroll 1
+#pragma unroll 2
         for (int c8 = 0; c8 < 16; ++c8) {                       // 16 chunks of 8 columns = 128 columns
           float hvv[8];
           if (live) {
@@ -544,127 +554,195 @@ reduce_partials_kernel(const float* __restrict__ partial, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// heads: rgb (3x128), sigma (1x256) and the 27 view-direction columns of the views layer -- fp32
+// heads: rgb (3x128), sigma (1x256) and the 27 view-direction columns of the views layer -- fp32.
+// Three streaming passes with wide loads (the data is read once; every thread keeps 8 x 16 B in flight),
+// per-block partial sums instead of atomics (deterministic), then one small reduction.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadTiles = 4;      // tiles (of 128 points) per block of head_grads_kernel
 struct HeadArgs {
   const float* d_raw;        // [P,4]
   const float* hv;           // [P,128]
   const uint8_t* acts;       // h8 images (act slot 8)
   const float* pe_dir;       // [n_rays, 27]
   const MlpConsts* gconsts;
-  float* head_partial;       // [gridDim.x][kHeadOut] per-block sums (no atomics: deterministic)
-  int64_t P, n_tiles;
-  int S;
+  float* head_partial;       // [rows][kHeadOut] per-block sums
+  float* gsum;               // [n_rays * segs][128]: per ray segment, sum over its points of g_v = (W_rgb^T d_rgb) * [hv > 0]
+  int64_t P, n_tiles, n_rays;
+  int S, segs;               // segs = ceil(S / kSegPoints) segments per ray
 };
 // per-block output layout: w_rgb [3][128] | view-direction columns [128][27] | w_alpha [256] | b_rgb [3], b_alpha
 constexpr int kHeadOffDir = 3 * kViewHidden, kHeadOffAlpha = kHeadOffDir + kViewHidden * kPeDir,
               kHeadOffBias = kHeadOffAlpha + kHidden, kHeadValid = kHeadOffBias + 4, kHeadOut = 4128;
+constexpr int kSegPoints = 32;           // head_rgb work unit: one warp, 32 consecutive points of one ray
+constexpr int kDirUnitsPerBlock = 64;
+constexpr int kSigmaTilesPerBlock = 4;
 
+// rgb head: warp = ray segment, lane = 4 views-hidden columns.  d W_rgb[c][j] = sum_p d_rgb[p][c] hv[p][j],
+// d b_rgb / d b_alpha = sum_p d_raw[p], and the per-segment sum of g_v for the view-direction columns.
+// Persistent: the grid is sized to the machine and the warps stride over the segments.
 __global__ void __launch_bounds__(256, 3)
-head_grads_kernel(const HeadArgs a) {
-  // threads 0..127: one views-hidden column each (rgb head, view-direction columns of the views
-  // layer); threads 128..255: two h8 columns each (sigma head).  A block owns kHeadTiles
-  // consecutive tiles, accumulates in registers and writes its sums to its own row of head_partial.
-  const int tid = threadIdx.x;
+head_rgb_kernel(const HeadArgs a) {
+  __shared__ float4 red[8][3][32];
+  __shared__ float4 redb[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const MlpConsts& cst = *a.gconsts;
-  __shared__ float4 sd[kTileM];                     // d_raw of the current tile
-  float wr[3] = {0.f, 0.f, 0.f}, d_wr[3] = {0.f, 0.f, 0.f}, d_dir[kPeDir];
-  float d_wa[2] = {0.f, 0.f}, d_b[4] = {0.f, 0.f, 0.f, 0.f};
+  float wr[3][4], acc[3][4];
 #pragma unroll
-  for (int i = 0; i < kPeDir; ++i) d_dir[i] = 0.f;
-  if (tid < kViewHidden) { wr[0] = cst.w_rgb[0][tid]; wr[1] = cst.w_rgb[1][tid]; wr[2] = cst.w_rgb[2][tid]; }
-  const int64_t tile0 = (int64_t)blockIdx.x * kHeadTiles;
-  for (int64_t tile = tile0; tile < tile0 + kHeadTiles && tile < a.n_tiles; ++tile) {
-    const int64_t p0 = tile * kTileM;
-    const int n = (int)((a.P - p0) < kTileM ? (a.P - p0) : kTileM);
-    __syncthreads();                                            // previous tile's readers are done with sd
-    if (tid < kTileM) sd[tid] = tid < n ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + p0 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    if (tid < kViewHidden) {
-      float gsum = 0.f;
-      int64_t ray = p0 / a.S;
-      int left = a.S - (int)(p0 - ray * a.S);                   // points left in the current ray (no per-point division)
-      for (int r0 = 0; r0 < n; r0 += 8) {
-        float h[8];
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {                           // 8 points in flight: all loads first
-          const int64_t p = p0 + ((r0 + q < n) ? r0 + q : n - 1);
-          h[q] = ldg_stream(a.hv + p * kViewHidden + tid);
-        }
+    for (int e = 0; e < 4; ++e) { wr[c][e] = cst.w_rgb[c][4 * lane + e]; acc[c][e] = 0.f; }
+  float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t n_units = a.n_rays * a.segs;
+  for (int64_t u = (int64_t)blockIdx.x * 8 + warp; u < n_units; u += (int64_t)gridDim.x * 8) {
+    const int64_t ray = u / a.segs;
+    const int r_begin = (int)(u - ray * a.segs) * kSegPoints;
+    const int n = (a.S - r_begin) < kSegPoints ? (a.S - r_begin) : kSegPoints;
+    const int64_t p0 = ray * a.S + r_begin;
+    float gs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r0 = 0; r0 < n; r0 += 8) {
+      float4 h[8], d[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (r0 + q >= n) break;
-          const float4 dq = sd[r0 + q];
-          if (left == 0) {                                      // ray boundary: fold the ray's sum of g_v
-#pragma unroll
-            for (int i = 0; i < kPeDir; ++i) d_dir[i] = fmaf(gsum, __ldg(a.pe_dir + ray * kPeDir + i), d_dir[i]);
-            gsum = 0.f; ++ray; left = a.S;
-          }
-          --left;
-          d_wr[0] = fmaf(dq.x, h[q], d_wr[0]); d_wr[1] = fmaf(dq.y, h[q], d_wr[1]); d_wr[2] = fmaf(dq.z, h[q], d_wr[2]);
-          if (h[q] > 0.f) gsum += fmaf(wr[0], dq.x, fmaf(wr[1], dq.y, wr[2] * dq.z));
-          if (tid == 0) { d_b[0] += dq.x; d_b[1] += dq.y; d_b[2] += dq.z; d_b[3] += dq.w; }
-        }
+      for (int q = 0; q < 8; ++q) {                             // all loads first
+        const int64_t p = p0 + (r0 + q < n ? r0 + q : n - 1);
+        h[q] = ldg_stream4(reinterpret_cast<const float4*>(a.hv + p * kViewHidden) + lane);
+        d[q] = __ldg(reinterpret_cast<const float4*>(a.d_raw) + p);
       }
 #pragma unroll
-      for (int i = 0; i < kPeDir; ++i) d_dir[i] = fmaf(gsum, __ldg(a.pe_dir + ray * kPeDir + i), d_dir[i]);
-    } else {
-      const int c0 = (tid - kViewHidden) * 2;                  // two h8 columns per thread
-      const uint8_t* img = a.acts + tile_img_offset(act_slot_kb0(8), 4, a.n_tiles, tile, c0 >> 6) + (c0 & 7) * 2;
-      const int ch = (c0 & 63) >> 3;
-      for (int r0 = 0; r0 < n; r0 += 8) {
-        uint32_t hh[8];
+      for (int q = 0; q < 8; ++q) {
+        if (r0 + q >= n) break;
+        const float hh[4] = {h[q].x, h[q].y, h[q].z, h[q].w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = (r0 + q < n) ? r0 + q : n - 1;
-          hh[q] = *reinterpret_cast<const uint32_t*>(img + r * 128 + ((ch ^ (r & 7)) << 4));
+        for (int e = 0; e < 4; ++e) {
+          acc[0][e] = fmaf(d[q].x, hh[e], acc[0][e]);
+          acc[1][e] = fmaf(d[q].y, hh[e], acc[1][e]);
+          acc[2][e] = fmaf(d[q].z, hh[e], acc[2][e]);
+          if (hh[e] > 0.f) gs[e] += fmaf(wr[0][e], d[q].x, fmaf(wr[1][e], d[q].y, wr[2][e] * d[q].z));
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float ds = sd[r0 + q].w;                        // zero past the end of the batch
-          d_wa[0] = fmaf(ds, __uint_as_float(hh[q] << 16), d_wa[0]);
-          d_wa[1] = fmaf(ds, __uint_as_float(hh[q] & 0xFFFF0000u), d_wa[1]);
-        }
+        db.x += d[q].x; db.y += d[q].y; db.z += d[q].z; db.w += d[q].w;
       }
     }
+    reinterpret_cast<float4*>(a.gsum + u * kViewHidden)[lane] = make_float4(gs[0], gs[1], gs[2], gs[3]);
   }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) red[warp][c][lane] = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+  if (lane == 0) redb[warp] = db;
+  __syncthreads();
   float* hp = a.head_partial + (size_t)blockIdx.x * kHeadOut;
-  if (tid < kViewHidden) {
+  if (threadIdx.x < 96) {                                       // (c, lane) -> 4 columns, summed over the 8 warps in order
+    const int c = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float4 t = red[0][c][l];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) hp[c * kViewHidden + tid] = d_wr[c];
+    for (int w = 1; w < 8; ++w) { const float4 v = red[w][c][l]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    reinterpret_cast<float4*>(hp + c * kViewHidden)[l] = t;
+  } else if (threadIdx.x == 96) {
+    float4 t = redb[0];
 #pragma unroll
-    for (int i = 0; i < kPeDir; ++i) hp[kHeadOffDir + tid * kPeDir + i] = d_dir[i];
-    if (tid == 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) hp[kHeadOffBias + c] = d_b[c];
-    }
-  } else {
-    const int c0 = (tid - kViewHidden) * 2;
-    hp[kHeadOffAlpha + c0] = d_wa[0];
-    hp[kHeadOffAlpha + c0 + 1] = d_wa[1];
+    for (int w = 1; w < 8; ++w) { t.x += redb[w].x; t.y += redb[w].y; t.z += redb[w].z; t.w += redb[w].w; }
+    hp[kHeadOffBias + 0] = t.x; hp[kHeadOffBias + 1] = t.y; hp[kHeadOffBias + 2] = t.z; hp[kHeadOffBias + 3] = t.w;
   }
 }
 
-// grad[dst(i)] += sum over blocks of head_partial[block][i]; four independent chains per thread hide the load latency
-__global__ void __launch_bounds__(128)
-reduce_heads_kernel(const float* __restrict__ hp, int n_blocks, float* __restrict__ grad, int off_wv, int off_walpha,
-                    int off_balpha, int off_wrgb, int off_brgb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kHeadValid) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= n_blocks; b += 4) {
-    s0 += hp[(size_t)(b + 0) * kHeadOut + i]; s1 += hp[(size_t)(b + 1) * kHeadOut + i];
-    s2 += hp[(size_t)(b + 2) * kHeadOut + i]; s3 += hp[(size_t)(b + 3) * kHeadOut + i];
+// view-direction columns of the views layer: d W_view[j][256 + i] = sum_segments gsum[seg][j] * pe_dir[ray(seg)][i]
+__global__ void __launch_bounds__(kViewHidden)
+head_dir_kernel(const HeadArgs a) {
+  __shared__ float pe[kDirUnitsPerBlock][kPeDir];
+  const int64_t n_units = a.n_rays * a.segs;
+  const int64_t u0 = (int64_t)blockIdx.x * kDirUnitsPerBlock;
+  const int n = (int)((n_units - u0) < kDirUnitsPerBlock ? (n_units - u0) : kDirUnitsPerBlock);
+  for (int e = threadIdx.x; e < n * kPeDir; e += blockDim.x) {
+    const int r = e / kPeDir, i = e - r * kPeDir;
+    pe[r][i] = __ldg(a.pe_dir + ((u0 + r) / a.segs) * kPeDir + i);
   }
-  for (; b < n_blocks; ++b) s0 += hp[(size_t)b * kHeadOut + i];
+  __syncthreads();
+  const int j = threadIdx.x;
+  float acc[kPeDir];
+#pragma unroll
+  for (int i = 0; i < kPeDir; ++i) acc[i] = 0.f;
+  for (int r = 0; r < n; r += 4) {
+    float g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = (r + q < n) ? __ldg(a.gsum + (u0 + r + q) * kViewHidden + j) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < kPeDir; ++i) acc[i] = fmaf(g[q], pe[(r + q < n) ? r + q : 0][i], acc[i]);
+  }
+  float* hp = a.head_partial + (size_t)blockIdx.x * kHeadOut + kHeadOffDir + j * kPeDir;
+#pragma unroll
+  for (int i = 0; i < kPeDir; ++i) hp[i] = acc[i];
+}
+
+// sigma head: d w_alpha[j] = sum_p dsigma[p] h8[p][j] over the saved (swizzled, bf16) h8 tile images.
+// warp = one K-block (64 columns) of a tile at a time; lane = (row & 3, 16-byte chunk): 512 B per load instruction.
+__global__ void __launch_bounds__(256, 4)
+head_sigma_kernel(const HeadArgs a) {
+  __shared__ float red[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = warp & 3, lc = lane & 7, rs = lane >> 3;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const int64_t tile0 = (int64_t)blockIdx.x * kSigmaTilesPerBlock;
+  for (int64_t tile = tile0 + (warp >> 2); tile < tile0 + kSigmaTilesPerBlock && tile < a.n_tiles; tile += 2) {
+    const uint8_t* img = a.acts + tile_img_offset(act_slot_kb0(8), 4, a.n_tiles, tile, kb);
+    const int64_t p0 = tile * kTileM;
+#pragma unroll 1
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+      uint4 v[8];
+      float ds[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = rs + 4 * (i0 + q);
+        v[q] = *reinterpret_cast<const uint4*>(img + r * 128 + ((lc ^ (r & 7)) << 4));
+        ds[q] = (p0 + r < a.P) ? __ldg(a.d_raw + (p0 + r) * 4 + 3) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] = fmaf(ds[q], __uint_as_float(w[e] << 16), acc[2 * e]);
+          acc[2 * e + 1] = fmaf(ds[q], __uint_as_float(w[e] & 0xFFFF0000u), acc[2 * e + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {                                 // the four row phases of a warp hold the same columns
+    acc[e] += __shfl_xor_sync(kFull, acc[e], 8);
+    acc[e] += __shfl_xor_sync(kFull, acc[e], 16);
+  }
+  if (rs == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lc * 8 + e] = acc[e];
+  }
+  __syncthreads();
+  const int c = threadIdx.x;                                    // column 0..255 = K-block c / 64: warps kb and kb + 4
+  a.head_partial[(size_t)blockIdx.x * kHeadOut + kHeadOffAlpha + c] = red[c >> 6][c & 63] + red[4 + (c >> 6)][c & 63];
+}
+
+// grad[dst(i)] += sum over the rows of head_partial that hold entry i (the rgb / dir / sigma passes use different
+// numbers of blocks).  One block per 32 entries; its 8 warps split the rows, then combine in a fixed order.
+__global__ void __launch_bounds__(256)
+reduce_heads_kernel(const float* __restrict__ hp, int n_rgb, int n_dir, int n_sigma, float* __restrict__ grad, int off_wv,
+                    int off_walpha, int off_balpha, int off_wrgb, int off_brgb) {
+  __shared__ float red[8][32];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
+  float s = 0.f;
+  if (i < kHeadValid) {
+    const int n_blocks = (i < kHeadOffDir || i >= kHeadOffBias) ? n_rgb : (i < kHeadOffAlpha ? n_dir : n_sigma);
+    for (int b = part; b < n_blocks; b += 8) s += hp[(size_t)b * kHeadOut + i];
+  }
+  red[part][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (part != 0 || i >= kHeadValid) return;
+#pragma unroll
+  for (int w = 1; w < 8; ++w) s += red[w][threadIdx.x];
   int dst;
   if (i < kHeadOffDir) dst = off_wrgb + i;
   else if (i < kHeadOffAlpha) { const int k = i - kHeadOffDir; dst = off_wv + (k / kPeDir) * (kHidden + kPeDir) + kHidden + k % kPeDir; }
   else if (i < kHeadOffBias) dst = off_walpha + (i - kHeadOffAlpha);
   else dst = (i - kHeadOffBias < 3) ? off_brgb + (i - kHeadOffBias) : off_balpha;
-  grad[dst] += (s0 + s1) + (s2 + s3);
+  grad[dst] += s;
 }
 
 // d(loss)/d(rgb) for loss = mean((rgb_c - gt)^2) + mean((rgb_f - gt)^2)  (training handler:291-305);
@@ -762,7 +840,23 @@ int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st) {
 // ---- launchers ------------------------------------------------------------------------------------
 size_t act_image_bytes(int64_t n_tiles) { return (size_t)kActKBlocksPerTile * n_tiles * kTileImgBytes; }
 int dw_partial_rows() { return kDwMaxParts; }
-size_t head_partial_bytes(int64_t n_tiles) { return (size_t)((n_tiles + kHeadTiles - 1) / kHeadTiles) * kHeadOut * sizeof(float); }
+// rows of head_partial: the most blocks any of the three head passes launches, plus the per-ray gsum [n_rays][128]
+static int head_rgb_blocks(int64_t n_units) {
+  const int64_t want = (n_units + 7) / 8, cap = 3 * (int64_t)num_sms();      // 3 resident blocks per SM
+  return (int)(want < cap ? want : cap);
+}
+static int64_t head_rows(int64_t n_tiles, int64_t n_units) {
+  int64_t r = head_rgb_blocks(n_units);
+  const int64_t b = (n_tiles + kSigmaTilesPerBlock - 1) / kSigmaTilesPerBlock, c = (n_units + kDirUnitsPerBlock - 1) / kDirUnitsPerBlock;
+  if (b > r) r = b;
+  if (c > r) r = c;
+  return r;
+}
+// worst case over the sample counts nwx_render_opts allows (S >= 11): segments per ray = ceil(S / 32) <= S / 11 + 1
+size_t head_partial_bytes(int64_t n_tiles, int64_t n_rays, int S) {
+  const int64_t n_units = n_rays * ((S + kSegPoints - 1) / kSegPoints);
+  return (size_t)(head_rows(n_tiles, n_units) * kHeadOut + n_units * kViewHidden) * sizeof(float);
+}
 size_t grad_image_bytes(int64_t n_tiles) { return (size_t)kGradKBlocksPerTile * (n_tiles + 1) * kTileImgBytes; }
 
 // Backward of one network: d_raw [P,4] -> flat gradient buffer `grad` (state_dict order, += into it).
@@ -850,13 +944,23 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     NWX_LAUNCHED();
   }
   HeadArgs h{};
+  const int64_t n_rays = a.P / a.S;
+  const int segs = (a.S + kSegPoints - 1) / kSegPoints;
+  const int64_t n_units = n_rays * segs;
   h.d_raw = a.d_raw; h.hv = a.hv; h.acts = a.acts; h.pe_dir = a.pe_dir; h.gconsts = net.gconsts;
-  h.head_partial = a.head_partial; h.P = a.P; h.n_tiles = tiles; h.S = a.S;
-  const int head_blocks = (int)((tiles + kHeadTiles - 1) / kHeadTiles);
-  head_grads_kernel<<<head_blocks, 256, 0, st>>>(h);
+  h.head_partial = a.head_partial; h.gsum = a.head_partial + head_rows(tiles, n_units) * kHeadOut;
+  h.P = a.P; h.n_tiles = tiles; h.n_rays = n_rays; h.S = a.S; h.segs = segs;
+  const int n_rgb = head_rgb_blocks(n_units);
+  const int n_dir = (int)((n_units + kDirUnitsPerBlock - 1) / kDirUnitsPerBlock);
+  const int n_sigma = (int)((tiles + kSigmaTilesPerBlock - 1) / kSigmaTilesPerBlock);
+  head_rgb_kernel<<<n_rgb, 256, 0, st>>>(h);
   NWX_LAUNCHED();
-  reduce_heads_kernel<<<(kHeadValid + 127) / 128, 128, 0, st>>>(a.head_partial, head_blocks, a.grad, g_flat.off[16], g_flat.off[20],
-                                                               g_flat.off[21], g_flat.off[22], g_flat.off[23]);
+  head_dir_kernel<<<n_dir, kViewHidden, 0, st>>>(h);
+  NWX_LAUNCHED();
+  head_sigma_kernel<<<n_sigma, 256, 0, st>>>(h);
+  NWX_LAUNCHED();
+  reduce_heads_kernel<<<(kHeadValid + 31) / 32, 256, 0, st>>>(a.head_partial, n_rgb, n_dir, n_sigma, a.grad, g_flat.off[16],
+                                                             g_flat.off[20], g_flat.off[21], g_flat.off[22], g_flat.off[23]);
   NWX_LAUNCHED();
   return NWX_OK;
 }
