@@ -315,7 +315,7 @@ extern "C" int nwx_adam_step(float* params, const float* grads, float* m, float*
 
 namespace {
 struct TrainPlan {
-  size_t acts_c, acts_f, masks_c, masks_f, gimg, head_partial, hv_c, hv_f, d_raw_c, d_raw_f, pe_dir, d_rgb_c, d_rgb_f, rgb_c, rgb_f, total;
+  size_t acts_c, acts_f, masks_c, masks_f, gimg, head_partial, fold, hv_c, hv_f, d_raw_c, d_raw_f, pe_dir, d_rgb_c, d_rgb_f, rgb_c, rgb_f, total;
 };
 TrainPlan plan_train(int64_t N, int Sc, int Ni) {
   TrainPlan p{};
@@ -329,6 +329,7 @@ TrainPlan plan_train(int64_t N, int Sc, int Ni) {
   p.masks_f = take(nwx::mask_image_bytes(tf));
   p.gimg = take(nwx::grad_image_bytes(tf));            // reused: coarse backward, then fine backward
   p.head_partial = take(nwx::head_partial_bytes(tf, N, Sf));  // reused like gimg
+  p.fold = take(nwx::kFoldScratchFloats * sizeof(float));
   p.hv_c = take((size_t)N * Sc * nwx::kViewHidden * 4);
   p.hv_f = take((size_t)N * Sf * nwx::kViewHidden * 4);
   p.d_raw_c = take((size_t)N * Sc * 16);
@@ -391,7 +392,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
   }
   auto fwd = [&](int which, const float* z, int S, float* raw) -> int {
     const nwx::PackedNet& net = ctx->net[which];
-    int r = nwx::launch_dirbias(net, io->rays + 8, rd, N, false, false, dirb, st);
+    int r = nwx::launch_dirbias(net, io->rays + 8, rd, N, false, true, dirb, st);    // folded views bias
     if (r) return r;
     nwx::MlpArgs a{};
     a.which = which;
@@ -425,6 +426,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     nwx::TrainBwdArgs b{};
     b.d_raw = d_raw[w]; b.hv = hv[w]; b.acts = acts[w]; b.masks = masks[w]; b.gimg = ts + tp.gimg; b.partial = ctx->partial;
     b.head_partial = reinterpret_cast<float*>(ts + tp.head_partial);
+    b.fold_scratch = reinterpret_cast<float*>(ts + tp.fold);
     b.pe_dir = pe_dir; b.grad = grads[w]; b.diag = ctx->diag; b.P = N * S[w]; b.S = S[w]; b.max_partials = ctx->n_partials;
     b.which = w;
     if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st))) return rc;

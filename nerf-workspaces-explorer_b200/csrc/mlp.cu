@@ -196,7 +196,6 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
   constexpr int kCG = kPair ? 2 : 1;
   constexpr int kNumChunks = num_chunks<kFold>();
   constexpr int kSeqLen = layers_per_tile<kFold>();      // accumulator hand-offs per tile and iteration
-  static_assert(!(kTrain && kFold), "the training forward keeps the reference's layer structure");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -529,19 +528,31 @@ __global__ void pack_dir_kernel(const float* __restrict__ wv, float* __restrict_
 // is the same function as nerf_model.py:64-70 with one bf16 rounding fewer (no rounded `feature`).
 __global__ void pack_fold_kernel(const float* __restrict__ wv, const float* __restrict__ wf,
                                  const float* __restrict__ bv, const float* __restrict__ bf,
-                                 uint8_t* __restrict__ wimg, float* __restrict__ bview_fold) {
+                                 uint8_t* __restrict__ wimg, float* __restrict__ bview_fold,
+                                 uint8_t* __restrict__ wimg_t /* training: transposed image for dX, or nullptr */) {
   const int kb = blockIdx.x;                       // K-block of the folded layer (64 input columns)
-  const int n0 = blockIdx.y * 8;                   // 8 output rows per block
+  const int n0 = blockIdx.y * 2;                   // 2 output rows per block: 256 blocks, one output per thread
   constexpr int kIn = kHidden + kPeDir;
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(wimg + kblock_offset(kFoldKBlock0 + kb));
-  for (int e = threadIdx.x; e < 8 * 64; e += blockDim.x) {
+  for (int e = threadIdx.x; e < 2 * 64; e += blockDim.x) {
     const int n = n0 + (e >> 6), c = e & 63, k = kb * 64 + c;
-    double acc = 0.0;
-    for (int m = 0; m < kHidden; ++m) acc += (double)wv[(size_t)n * kIn + m] * (double)wf[(size_t)m * kHidden + k];
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};          // four independent chains: the loop is latency-bound
+#pragma unroll 4
+    for (int m = 0; m < kHidden; m += 4)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a4[q] += (double)wv[(size_t)n * kIn + m + q] * (double)wf[(size_t)(m + q) * kHidden + k];
+    const double acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     const int chunk = (c >> 3) ^ (n & 7);
-    img[n * 64 + chunk * 8 + (c & 7)] = __float2bfloat16_rn((float)acc);
+    const __nv_bfloat16 w = __float2bfloat16_rn((float)acc);
+    img[n * 64 + chunk * 8 + (c & 7)] = w;
+    if (wimg_t) {
+      // dX step 0: d h8[p][i] = sum_o G_v[p][o] W_fold[o][i]  =>  B[row i][k = o]; K-block o / 64 of [256 x 64]
+      __nv_bfloat16* timg = reinterpret_cast<__nv_bfloat16*>(wimg_t + (size_t)(n >> 6) * kKBlockBytes);
+      const int o = n & 63;
+      timg[k * 64 + (((o >> 3) ^ (k & 7)) << 3) + (o & 7)] = w;
+    }
   }
-  if (kb == 0 && threadIdx.x < 8) {
+  if (kb == 0 && threadIdx.x < 2) {
     const int n = n0 + threadIdx.x;
     double acc = (double)bv[n];
     for (int m = 0; m < kHidden; ++m) acc += (double)wv[(size_t)n * kIn + m] * (double)bf[m];
@@ -552,7 +563,7 @@ __global__ void pack_fold_kernel(const float* __restrict__ wv, const float* __re
 // Device-side part of packing (no host synchronisation): swizzled bf16 K-block images, the transposed
 // fp32 view-direction weights and the views bias.  t: 24 device pointers in state_dict order:
 // pts.{0..7}.{w,b} (0..15), views.{w,b} (16,17), feature (18,19), alpha (20,21), rgb (22,23).
-int pack_network_images(PackedNet& net, const float* const* t, bool with_fold, cudaStream_t st) {
+int pack_network_images(PackedNet& net, const float* const* t, bool with_fold, cudaStream_t st, uint8_t* fold_t) {
   if (!net.wimg) NWX_CUDA_TRY(cudaMalloc(&net.wimg, kWeightImageBytes));
   if (!net.wdir_t) NWX_CUDA_TRY(cudaMalloc(&net.wdir_t, sizeof(float) * kPeDir * kViewHidden));
   if (!net.bview) NWX_CUDA_TRY(cudaMalloc(&net.bview, sizeof(float) * kViewHidden));
@@ -567,7 +578,7 @@ int pack_network_images(PackedNet& net, const float* const* t, bool with_fold, c
   NWX_LAUNCHED();
   NWX_CUDA_TRY(cudaMemcpyAsync(net.bview, t[17], sizeof(float) * kViewHidden, cudaMemcpyDeviceToDevice, st));
   if (with_fold) {
-    pack_fold_kernel<<<dim3(4, kViewHidden / 8), 256, 0, st>>>(t[16], t[18], t[17], t[19], net.wimg, net.bview_fold);
+    pack_fold_kernel<<<dim3(4, kViewHidden / 2), 128, 0, st>>>(t[16], t[18], t[17], t[19], net.wimg, net.bview_fold, fold_t);
     NWX_LAUNCHED();
   }
   return NWX_OK;
@@ -688,12 +699,13 @@ int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st)
   }
 }
 
-// Training forward: same kernel (CTA pair, resident weights), biases/heads read from device memory
-// (they change every step), tensor-core operands saved as tile images for the backward.
+// Training forward: same kernel (CTA pair, resident weights, folded feature layer -- re-folded from the master
+// weights by every train_pack), biases/heads read from device memory (they change every step), tensor-core
+// operands saved as tile images for the backward.
 int launch_mlp_train_forward(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   if (args.P <= 0) return NWX_OK;
   args.gconsts = net.gconsts;
-  return launch_variant<true, true, 4, false, true>(net, args, st);
+  return launch_variant<true, true, 4, false, true, true>(net, args, st);
 }
 
 }  // namespace nwx

@@ -46,7 +46,7 @@ struct MlpConsts {
 constexpr int kTileImgBytes = 16384;
 __host__ __device__ constexpr int act_slot_nkb(int s) { return s == 0 ? 1 : 4; }
 __host__ __device__ constexpr int act_slot_kb0(int s) { return s == 0 ? 0 : 1 + 4 * (s - 1); }
-constexpr int kActKBlocksPerTile = 37;
+constexpr int kActKBlocksPerTile = 33;      // slots 0..8 (slot 9, the feature output, is not materialised: folded)
 __host__ __device__ constexpr int grad_slot_nkb(int s) { return s == 0 ? 2 : 4; }
 __host__ __device__ constexpr int grad_slot_kb0(int s) { return s == 0 ? 0 : 2 + 4 * (s - 1); }
 constexpr int kGradKBlocksPerTile = 38;
@@ -68,6 +68,7 @@ struct PackedNet {
   MlpConsts consts;                  // host copy
   MlpConsts* gconsts = nullptr;      // device copy (training kernels read it through a pointer)
   uint8_t* wimg_t = nullptr;         // device: transposed-weight K-block images for the dX kernel
+  const float* master = nullptr;     // device: flat fp32 master parameters given to the last train_pack (caller-owned)
   bool loaded = false;
   bool consts_stale = false;         // host consts older than the device master weights (training)
 };
@@ -92,7 +93,8 @@ struct MlpArgs {
 };
 
 int pack_network(PackedNet& net, const float* const* tensors, cudaStream_t st);
-int pack_network_images(PackedNet& net, const float* const* tensors, bool with_fold, cudaStream_t st);
+int pack_network_images(PackedNet& net, const float* const* tensors, bool with_fold, cudaStream_t st,
+                        uint8_t* fold_t = nullptr);
 inline bool variant_folds(int variant) { return variant <= 1; }
 int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, bool fold,
                    float* out, cudaStream_t st);
@@ -108,6 +110,7 @@ struct TrainBwdArgs {
   uint8_t* gimg;             // gradient image scratch (grad_image_bytes)
   float* partial;            // [max_partials][NWX_PARAMS_PER_NET] dW partials (zero-initialised once)
   float* head_partial;       // head_partial_bytes(n_tiles): per-block sums of the head gradients
+  float* fold_scratch;       // kFoldScratchFloats: d W_fold [128 x 256] and d b_fold [128]
   const float* pe_dir;       // [n_rays,27] embedded view directions
   float* grad;               // flat gradient buffer of this network (accumulated into)
   uint32_t* diag;
@@ -120,6 +123,7 @@ size_t act_image_bytes(int64_t n_tiles);
 size_t grad_image_bytes(int64_t n_tiles);
 size_t head_partial_bytes(int64_t n_tiles, int64_t n_rays, int S);
 int dw_partial_rows();
+constexpr size_t kFoldScratchFloats = (size_t)kViewHidden * kHidden + kViewHidden;
 inline size_t mask_image_bytes(int64_t n_tiles) { return (size_t)(n_tiles + 1) * kMaskTileBytes; }
 const int* flat_offsets();
 int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st);

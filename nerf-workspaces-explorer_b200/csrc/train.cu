@@ -23,25 +23,28 @@ namespace nwx {
 
 // ------------------------------------------------------------------------------------------------
 // transposed weight images for dX:  dH_in[p][i] = sum_o G[p][o] W[o][i]  =>  B[n=i][k=o] = W[o][i]
-// steps: 0 = views (K = 128 -> 2 K-blocks), 1 = feature, 2..8 = pts layers 7..1 (4 K-blocks each)
+// steps: 0 = folded views layer W_fold = W_view[:, :256] . W_feature (K = 128 -> 2 K-blocks, written by
+// pack_fold_kernel), 1..7 = pts layers 7..1 (4 K-blocks each).  The training forward runs the folded layer, so
+// the backward differentiates exactly that function; the chain rule back to W_view / W_feature / b_feature is
+// applied to the accumulated d W_fold / d b_fold by fold_grads_*_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDxSteps = 9;
-constexpr int kDxKBlocks = 2 + 8 * 4;     // 34 images of [256 x 64]
+constexpr int kDxSteps = 8;
+constexpr int kDxKBlocks = 2 + 7 * 4;     // 30 images of [256 x 64]
 __host__ __device__ constexpr int dx_step_nkb(int s) { return s == 0 ? 2 : 4; }
 __host__ __device__ constexpr int dx_step_kb0(int s) { return s == 0 ? 0 : 2 + 4 * (s - 1); }
 
 struct PackTSrc {
-  const float* w[kDxSteps];   // views, feature, pts7, pts6, pts5, pts4, pts3, pts2, pts1
+  const float* w[kDxSteps];   // (unused: fold), pts7, pts6, pts5, pts4, pts3, pts2, pts1
 };
 
 __global__ void pack_weights_t_kernel(PackTSrc src, uint8_t* __restrict__ wimg_t) {
-  const int g = blockIdx.x;
+  const int g = blockIdx.x + 2;             // K-blocks 0, 1 (step 0) come from pack_fold_kernel
   int s = 0, kb = g;
   while (kb >= dx_step_nkb(s)) { kb -= dx_step_nkb(s); ++s; }
   // source tensor [out, in_dim]; dX needs input columns c0 .. c0+255 (the h part) only
-  const int in_dim = (s == 0) ? kHidden + kPeDir : (s == 4 ? kPeXyz + kHidden : kHidden);   // s==4 is pts layer 5
-  const int c0 = (s == 4) ? kPeXyz : 0;
-  const int outs = (s == 0) ? kViewHidden : kHidden;
+  const int in_dim = (s == 3) ? kPeXyz + kHidden : kHidden;   // s == 3 is pts layer 5
+  const int c0 = (s == 3) ? kPeXyz : 0;
+  const int outs = kHidden;
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(wimg_t + (size_t)g * kKBlockBytes);
   for (int e = threadIdx.x; e < kHidden * 64; e += blockDim.x) {
     const int n = e >> 6, c = e & 63;                 // n = input feature (row of B), c = k within the block
@@ -200,8 +203,8 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
             const int nkb = dx_step_nkb(s);
             for (int t = 0; t < 2; ++t) {
               if (s == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
-              // a_ready[t] completes once per step epilogue: phase index = 9*it + s - 1
-              if (s != 0 || it != 0) mbar_wait(sbase + L::a_ready + 8 * t, (9 * it + s + 1) & 1, wc);
+              // a_ready[t] completes once per step epilogue: phase index = kDxSteps*it + s - 1
+              if (s != 0 || it != 0) mbar_wait(sbase + L::a_ready + 8 * t, (kDxSteps * it + s + 1) & 1, wc);
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + t * kHidden;
               for (int kb = 0; kb < nkb; ++kb) {
@@ -306,7 +309,7 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
       for (int s = 0; s < kDxSteps; ++s) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(sbase + L::acc_full + 8 * t, (9 * it + s) & 1, wc);
+          mbar_wait(sbase + L::acc_full + 8 * t, (kDxSteps * it + s) & 1, wc);
           tc_fence_after();
           const int64_t tile = tile_of(it, t);
           // dead tiles (past the end) still run so the barrier protocol stays uniform; they write
@@ -314,19 +317,19 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           const int64_t wt = tile < args.n_tiles ? tile : args.n_tiles;
           const uint32_t d_tmem = lane_addr + t * kHidden;
           const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
-          uint8_t* grow = args.grads + tile_img_offset(grad_slot_kb0(s + 1), 4, args.n_tiles + 1, wt, 0) + row * 128;
-          // mask = activation that the produced gradient flows into: step 1 -> h8 (act slot 8) ... step 8 -> h1
+          // step s produces G_{8-s} = dL/d(pre-activation of pts layer 7-s) -> grad slot s + 2 (slot 1 is unused)
+          uint8_t* grow = args.grads + tile_img_offset(grad_slot_kb0(s + 2), 4, args.n_tiles + 1, wt, 0) + row * 128;
+          // mask = ReLU' of the activation the produced gradient flows into: step 0 -> h8 (pts layer 7) ... step 7 -> h1
           const int64_t mt = tile < args.n_tiles ? tile : 0;
           const uint32_t* mrow = reinterpret_cast<const uint32_t*>(
-                                     reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(mt, s == 0 ? 0 : 8 - s)) + row;
-          // Steps 0..6 leave their G tile in smem (next step's A operand) and save it with ONE TMA
-          // store; steps 7 and 8 store per thread: after step 8's MMA the G_views producers reuse the
+                                     reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(mt, 7 - s)) + row;
+          // All but the last two steps leave their G tile in smem (next step's A operand) and save it with ONE
+          // TMA store; the last two store per thread: after the last MMA the G_views producers reuse the
           // buffer, and they cannot wait on another thread's bulk group.
           const bool via_tma = s < kDxSteps - 2;
           if (warp == 8 && lane == 0) bulk_wait_read<1>();      // earlier store of this buffer has finished reading it
           named_bar_sync(3, 256);
-          if (s == 0) bwd_epilogue<kBwdLinear>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, 0.f);
-          else if (s == 1) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, dsig[t]);
+          if (s == 0) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, dsig[t]);
           else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, !via_tma, row, wg, mrow, grow, 0.f);
           fence_proxy_async_smem();
           tc_fence_before();
@@ -335,13 +338,13 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           if (via_tma) {
             named_bar_sync(3, 256);                             // every warp's tile writes are fenced
             if (warp == 8 && lane == 0)
-              bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 1), 4, args.n_tiles + 1, wt, 0),
+              bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 2), 4, args.n_tiles + 1, wt, 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
           }
           // the next step's ReLU' bit words (four 128 B lines per warp): pull them into L2 now, one MMA
           // step ahead, so the epilogue's loads do not wait on DRAM
           if (s + 1 < kDxSteps && tile < args.n_tiles && lane == 0) {
-            const uint8_t* nm = reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(tile, 7 - s) +
+            const uint8_t* nm = reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(tile, 6 - s) +
                                 (size_t)(wg * 4) * 512 + quad * 128;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + cc * 512));
@@ -361,7 +364,7 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
 // ------------------------------------------------------------------------------------------------
 // Job-major: every CTA works on ONE (G, X) pair for its whole life -- a share of the tiles, one dW in TMEM, one
 // flush at the end -- instead of walking all 11 jobs with a TMEM flush (and an idle tensor pipe) between them.
-constexpr int kDwJobs = 11;
+constexpr int kDwJobs = 10;
 constexpr int kDwMaxParts = 16;    // most CTAs one job is split over
 struct DwJob {
   int g_kb0, g_nkb;          // gradient image slot (K-block offset, count): out features = 64 * g_nkb
@@ -541,7 +544,8 @@ reduce_partials_kernel(const float* __restrict__ partial, const __grid_constant_
   for (int j = 0; j < kDwJobs; ++j) {
     const DwJob& jb = tab.job[j];
     const int rows = 64 * jb.g_nkb;
-    if (i >= jb.w_off && i < jb.w_off + rows * jb.in_stride) {
+    // the last job's weight region holds d W_fold, which is not a parameter: fold_grads_*_kernel consume it
+    if (j != kDwJobs - 1 && i >= jb.w_off && i < jb.w_off + rows * jb.in_stride) {
       const int col = (i - jb.w_off) % jb.in_stride;
       if (col >= jb.col0 && col < jb.col0 + jb.n_valid) { n_parts = jb.ncta; break; }
     }
@@ -551,6 +555,79 @@ reduce_partials_kernel(const float* __restrict__ partial, const __grid_constant_
   float s = 0.f;
   for (int c = 0; c < n_parts; ++c) s += partial[(size_t)c * NWX_PARAMS_PER_NET + i];
   grad[i] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain rule through the fold W_fold = V . F, b_fold = b_view + V . b_F   (V = W_view[:, :256] [128 x 256],
+// F = W_feature [256 x 256]):   dV = dW_fold . F^T + d b_fold (x) b_F,   dF = V^T . dW_fold,   d b_F = V^T . d b_fold,
+// d b_view = d b_fold
+// ------------------------------------------------------------------------------------------------
+// fold[o][k] = sum over the job's CTAs of partial[part][w_off + o * 283 + k]; fold[128*256 + o] likewise for d b_fold
+__global__ void __launch_bounds__(256)
+fold_sum_kernel(const float* __restrict__ partial, int n_parts, int w_off, int b_off, float* __restrict__ fold) {
+  const int o = blockIdx.x, k = threadIdx.x;
+  float s = 0.f;
+  for (int c = 0; c < n_parts; ++c) s += partial[(size_t)c * NWX_PARAMS_PER_NET + w_off + o * (kHidden + kPeDir) + k];
+  fold[o * kHidden + k] = s;
+  if (k == 0) {
+    float b = 0.f;
+    for (int c = 0; c < n_parts; ++c) b += partial[(size_t)c * NWX_PARAMS_PER_NET + b_off + o];
+    fold[kViewHidden * kHidden + o] = b;
+  }
+}
+
+// dF[m][k] += sum_o V[o][m] fold[o][k]  (4 rows m per block);  d b_F[m] += sum_o V[o][m] dbfold[o]
+__global__ void __launch_bounds__(256)
+fold_grads_feature_kernel(const float* __restrict__ wv, const float* __restrict__ fold, float* __restrict__ d_wf,
+                          float* __restrict__ d_bf) {
+  __shared__ float v[kViewHidden][4];
+  const int m0 = blockIdx.x * 4, k = threadIdx.x;
+  for (int e = threadIdx.x; e < kViewHidden * 4; e += blockDim.x) v[e >> 2][e & 3] = wv[(size_t)(e >> 2) * (kHidden + kPeDir) + m0 + (e & 3)];
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int o = 0; o < kViewHidden; ++o) {
+    const float f = fold[o * kHidden + k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = fmaf(v[o][q], f, acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) d_wf[(size_t)(m0 + q) * kHidden + k] += acc[q];
+  if (k < 4) {
+    float b = 0.f;
+    for (int o = 0; o < kViewHidden; ++o) b = fmaf(v[o][k], fold[kViewHidden * kHidden + o], b);
+    d_bf[m0 + k] += b;
+  }
+}
+
+// dV[o][m] += sum_k fold[o][k] F[m][k] + dbfold[o] b_F[m]  (b_fold = b_view + V b_F depends on V too):
+// 32 x 32 output tile per block, both operands staged through smem
+__global__ void __launch_bounds__(256)
+fold_grads_view_kernel(const float* __restrict__ wf, const float* __restrict__ bf, const float* __restrict__ fold,
+                       float* __restrict__ d_wv) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int o0 = blockIdx.y * 32, m0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows of threads: 4 outputs each
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < kHidden; k0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sa[ty + 8 * q][tx] = fold[(o0 + ty + 8 * q) * kHidden + k0 + tx];
+      sb[ty + 8 * q][tx] = wf[(size_t)(m0 + ty + 8 * q) * kHidden + k0 + tx];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float b = sb[tx][kk];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(sa[ty + 8 * q][kk], b, acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    d_wv[(size_t)(o0 + ty + 8 * q) * (kHidden + kPeDir) + m0 + tx] +=
+        fmaf(fold[kViewHidden * kHidden + o0 + ty + 8 * q], bf[m0 + tx], acc[q]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -822,13 +899,13 @@ int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st) {
   if (!net.gconsts) NWX_CUDA_TRY(cudaMalloc(&net.gconsts, sizeof(MlpConsts)));
   TensorTable tab;
   for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) tab.t[i] = params_flat + g_flat.off[i];
-  int rc = pack_network_images(net, tab.t, false, st);     // training keeps the reference's layer structure
+  int rc = pack_network_images(net, tab.t, true, st, net.wimg_t);   // + folded views layer, forward and transposed
   if (rc) return rc;
+  net.master = params_flat;
   PackTSrc ts;
-  ts.w[0] = tab.t[16];
-  ts.w[1] = tab.t[18];
-  for (int s = 2; s < kDxSteps; ++s) ts.w[s] = tab.t[2 * (9 - s)];     // pts layers 7..1
-  pack_weights_t_kernel<<<kDxKBlocks, 256, 0, st>>>(ts, net.wimg_t);
+  ts.w[0] = nullptr;
+  for (int s = 1; s < kDxSteps; ++s) ts.w[s] = tab.t[2 * (8 - s)];     // pts layers 7..1
+  pack_weights_t_kernel<<<kDxKBlocks - 2, 256, 0, st>>>(ts, net.wimg_t);
   NWX_LAUNCHED();
   fill_consts_kernel<<<(9 * kHidden + 255) / 256, 256, 0, st>>>(tab, net.gconsts);
   NWX_LAUNCHED();
@@ -908,8 +985,9 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     job(6, 4, 5, 10, 319, 63, 256, -1);            // pts5, h5 columns
     job(7, 3, 6, 12, 256, 0, 256, 13);             // pts6: G7 x h6
     job(8, 2, 7, 14, 256, 0, 256, 15);             // pts7: G8 x h7
-    job(9, 1, 8, 18, 256, 0, 256, 19);             // feature: d_f x h8
-    job(10, 0, 9, 16, 283, 0, 256, 17);            // views: G_v x f
+    // folded views layer: d W_fold = G_v^T h8 lands where d W_view[:, :256] lives (same shape and stride);
+    // fold_grads_*_kernel then turns it into d W_view[:, :256], d W_feature, d b_feature
+    job(9, 0, 8, 16, 283, 0, 256, 17);
     // CTAs per job in proportion to the bytes a job streams per tile (largest remainder), at most
     // kDwMaxParts and never more than there are tiles
     int units = 0, given = 0, parts[kDwJobs];
@@ -941,6 +1019,16 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     DwJobTable tab;
     for (int j = 0; j < kDwJobs; ++j) tab.job[j] = w.job[j];
     reduce_partials_kernel<<<(NWX_PARAMS_PER_NET + 255) / 256, 256, 0, st>>>(a.partial, tab, a.grad);
+    NWX_LAUNCHED();
+    // folded views layer -> d W_view[:, :256], d W_feature, d b_feature (fp32, against the master weights)
+    if (!net.master) return NWX_E_NO_WEIGHTS;
+    const DwJob& fj = w.job[kDwJobs - 1];
+    fold_sum_kernel<<<kViewHidden, kHidden, 0, st>>>(a.partial, fj.ncta, fj.w_off, fj.b_off, a.fold_scratch);
+    NWX_LAUNCHED();
+    fold_grads_feature_kernel<<<kHidden / 4, 256, 0, st>>>(net.master + off[16], a.fold_scratch, a.grad + off[18], a.grad + off[19]);
+    NWX_LAUNCHED();
+    fold_grads_view_kernel<<<dim3(kHidden / 32, kViewHidden / 32), 256, 0, st>>>(net.master + off[18], net.master + off[19], a.fold_scratch,
+                                                                                   a.grad + off[16]);
     NWX_LAUNCHED();
   }
   HeadArgs h{};
