@@ -54,41 +54,64 @@ def synthetic_setup():
 
 # --------------------------------------------------------------------------- clocks ----
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and clock-event reasons of one GPU sampled every 10 ms through NVML while the timed
+    region runs (a thread in this process; `nvidia-smi -lms` cannot sample a sub-second region densely)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._stop, self._thread, self._h, self._nv = index, [], threading.Event(), None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:  # noqa: BLE001
+            self._nv = None
+
+    @staticmethod
+    def _physical_index(local: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                return int(ids[local])
+        return local
+
+    def _loop(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, pw, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self._nv is None:
+            return
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        smax = max((float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()), default=None)
-        power = max((float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "power_w_max": power,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self._nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thread.join()
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({name for r in self.rows for name, bit in self.REASONS if r[2] & bit})
+        try:
+            smax = self._nv.nvmlDeviceGetMaxClockInfo(self._h, self._nv.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            smax = None
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_min_mhz": float(sm[0]) if sm else None,
+                "sm_max_mhz": float(smax) if smax else None,
+                "power_w_max": max((r[1] for r in self.rows), default=None), "samples": len(sm), "reasons": reasons,
+                "how": "NVML, 10 ms period, timed region only"}
 
 
 # --------------------------------------------------------------------- CPU reference ----

@@ -223,8 +223,10 @@ int nwx_ctx_stage_ms(nwx_ctx* ctx, float* ms_out);
 /* ---- introspection for bench/tests --------------------------------------------------------- */
 /* Number of kernels this library has launched since load (all contexts). */
 int64_t nwx_launch_count(void);
-/* MLP kernel variant: 0 = auto (CTA pair, resident weights), 2 = CTA pair streaming, 3 = single
- * CTA (cta_group::1).  Tests use it to cross-check variants; see DESIGN.md. */
+/* MLP kernel variant: 0/1 = production (CTA pair, resident weights, _feature_linear folded into the
+ * views layer at weight-load time -- exact algebra, nerf_model.py:64-68 has no non-linearity between
+ * them), 2 = CTA pair streaming, 3 = single CTA (cta_group::1), 4 = as 1 with the reference's layer
+ * structure (no fold).  Tests use it to cross-check variants; see DESIGN.md. */
 int nwx_set_mlp_variant(nwx_ctx* ctx, int variant);
 /* Diagnostics: tap the post-activation fp32 output of tensor-core layer `layer` (0..9) of
  * subsequent MLP launches into out [P,256] (NULL = off); register a host-mapped uint32[4] that
