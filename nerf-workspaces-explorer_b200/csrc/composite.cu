@@ -36,6 +36,12 @@ __device__ __forceinline__ float sigmoidf_rn(float x) {        // torch.sigmoid:
   return __frcp_rn(__fadd_rn(1.0f, expf(-x)));                 // correctly rounded 1/y == correctly rounded reciprocal
 }
 
+// Forward colour path: sigmoid to ~1e-7 absolute (MUFU.EX2 + MUFU.RCP) instead of the correctly rounded
+// expf + reciprocal (~35 instructions, three per sample: they made the forward instruction-bound).  Colours
+// carry the 1e-3 tolerance of the bf16 MLP; the weights (alpha, transmittance), which decide the
+// importance-sampling indices, keep the exact op-for-op arithmetic.  The backward keeps sigmoidf_rn.
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 struct RaySample {
   float c[3];     // sigmoid(raw rgb)
   float alpha;    // 1 - exp(-relu(sigma+noise)*dist)
@@ -142,9 +148,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const float w = __fmul_rn(alpha, T);
       if (s < S) {
         if (weights) weights[ray * S + s] = w;
-        a_r += __fmul_rn(w, sigmoidf_rn(rw[j].x));                          // :62,:84
-        a_g += __fmul_rn(w, sigmoidf_rn(rw[j].y));
-        a_b += __fmul_rn(w, sigmoidf_rn(rw[j].z));
+        a_r += __fmul_rn(w, sigmoidf_fast(rw[j].x));                        // :62,:84
+        a_g += __fmul_rn(w, sigmoidf_fast(rw[j].y));
+        a_b += __fmul_rn(w, sigmoidf_fast(rw[j].z));
         a_d += __fmul_rn(w, zr[j]);
         a_w += w;
       }

@@ -110,14 +110,16 @@ enum { kEpiRelu = 0, kEpiReluSigma = 1, kEpiLinear = 2 };
 // accumulator -> +bias -> (ReLU) -> bf16 -> the next layer's swizzled A-operand tile.
 // Returns this half's partial of the fp32 sigma head when kMode == kEpiReluSigma.
 // One 32-column chunk of the hidden-layer epilogue: +bias -> (ReLU) -> bf16 -> swizzled A tile.
-template <int kMode, bool kTap, bool kSave>
-__device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, const uint32_t (&v)[32], int col, uint32_t hrow,
+template <int kMode, bool kTap, bool kSave, int W>
+__device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, const uint32_t (&v)[W], int col, uint32_t hrow,
                                                int row, float* tap_row, uint8_t* grow /* mask words of (tile, layer) */,
                                                float& sig) {
-  uint32_t pk[16];
+  static_assert(W == 32 || W == 16, "chunk of 32 columns (8 epilogue warps) or 16 (16 epilogue warps)");
+  static_assert(!kSave || W == 32, "the training masks are one word per 32 columns");
+  uint32_t pk[W / 2];
   const bool no_sts = kTap && hrow == 0;          // timing experiment (debug instantiation only)
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
+  for (int j = 0; j < W; j += 2) {
     const float a = __uint_as_float(v[j]) + cst.bias[l][col + j];
     const float b = __uint_as_float(v[j + 1]) + cst.bias[l][col + j + 1];
     if (kMode == kEpiReluSigma) {                  // sigma head on fp32 relu(h7), nerf_model.py:63
@@ -134,12 +136,12 @@ __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, cons
   const int j0 = (col & 63) >> 3;
   if (!no_sts) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < W / 8; ++q)
       st_shared_v4(kbase + (((j0 + q) ^ (row & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
   } else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) {
-    st_shared_v4(kbase, pk[0], pk[5], pk[10], pk[15]);      // keeps the math alive
+    st_shared_v4(kbase, pk[0], pk[3], pk[5], pk[7]);        // keeps the math alive
   }
-  if (kSave && kMode != kEpiLinear) {
+  if constexpr (kSave && kMode != kEpiLinear && W == 32) {
     // training: ReLU' of this row's 32 columns as one word for the dX kernel (bit j / 16 + j = low / high
     // half of packed word j is non-zero), so the backward reads 4 B instead of 64 B of activations here.
     // h >= +0 after the ReLU, so h + 0x7FFF carries into bit 15 exactly when h != 0.
@@ -150,33 +152,38 @@ __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, cons
   }
 }
 
-// Hidden-layer epilogue of one thread (= one point / TMEM lane) over its 128-column half, software
-// pipelined two deep: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed (the
-// epilogue is latency-bound: 2 epilogue warps per scheduler), and the bias loads are free to move
-// above the TMEM wait.  Returns this half's partial of the fp32 sigma head (kEpiReluSigma).
-template <int kMode, bool kTap, bool kSave>
+// Hidden-layer epilogue of one thread (= one point / TMEM lane) over its 4 * W columns (8 epilogue warps: a
+// 128-column half in chunks of 32; 16 epilogue warps: a 64-column quarter in chunks of 16), software pipelined
+// two deep: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed (the epilogue is latency-bound:
+// 2-4 epilogue warps per scheduler), and the bias loads are free to move above the TMEM wait.  Returns this
+// thread's partial of the fp32 sigma head (kEpiReluSigma).
+template <int kMode, bool kTap, bool kSave, int W>
 __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, uint32_t d_tmem, uint32_t hrow,
-                                                 int row, int wg, float* tap_row, uint8_t* grow) {
+                                                 int row, int wg, float* tap_row, uint8_t* grow, bool dbg_half = false) {
   float sig = 0.f;
-  const int col0 = wg * 128;
-  uint32_t va[32], vb[32];
-  tmem_ld32(d_tmem + col0, va);
+  const int col0 = wg * 4 * W;
+  uint32_t va[W], vb[W];
+  tmem_ld(d_tmem + col0, va);
   tmem_wait_ld_dep(va);
-  tmem_ld32(d_tmem + col0 + 32, vb);
-  epilogue_chunk<kMode, kTap, kSave>(cst, l, va, col0, hrow, row, tap_row, grow, sig);
+  tmem_ld(d_tmem + col0 + W, vb);
+  epilogue_chunk<kMode, kTap, kSave, W>(cst, l, va, col0, hrow, row, tap_row, grow, sig);
   tmem_wait_ld_dep(vb);
-  tmem_ld32(d_tmem + col0 + 64, va);
-  epilogue_chunk<kMode, kTap, kSave>(cst, l, vb, col0 + 32, hrow, row, tap_row, grow, sig);
+  if (kTap && dbg_half) {            // timing experiment: half the epilogue (what twice the epilogue warps would leave per thread)
+    epilogue_chunk<kMode, kTap, kSave, W>(cst, l, vb, col0 + W, hrow, row, tap_row, grow, sig);
+    return sig;
+  }
+  tmem_ld(d_tmem + col0 + 2 * W, va);
+  epilogue_chunk<kMode, kTap, kSave, W>(cst, l, vb, col0 + W, hrow, row, tap_row, grow, sig);
   tmem_wait_ld_dep(va);
-  tmem_ld32(d_tmem + col0 + 96, vb);
-  epilogue_chunk<kMode, kTap, kSave>(cst, l, va, col0 + 64, hrow, row, tap_row, grow, sig);
+  tmem_ld(d_tmem + col0 + 3 * W, vb);
+  epilogue_chunk<kMode, kTap, kSave, W>(cst, l, va, col0 + 2 * W, hrow, row, tap_row, grow, sig);
   tmem_wait_ld_dep(vb);
-  epilogue_chunk<kMode, kTap, kSave>(cst, l, vb, col0 + 96, hrow, row, tap_row, grow, sig);
+  epilogue_chunk<kMode, kTap, kSave, W>(cst, l, vb, col0 + 3 * W, hrow, row, tap_row, grow, sig);
   return sig;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold, int kEpiWarps>
+__global__ void __launch_bounds__(256 + 32 * kEpiWarps, 1)
 mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst_param) {
   using L = SmemLayout<kPair, kStages>;
   const MlpConsts& cst = kTrain ? c_fwd_train_consts[args.which] : cst_param;
@@ -194,6 +201,10 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     }
   };
   constexpr int kCG = kPair ? 2 : 1;
+  constexpr int kEpiGroups = kEpiWarps / 4;              // column groups: 2 x 128 columns or 4 x 64 columns
+  constexpr int kW = 256 / kEpiGroups / 4;               // epilogue chunk width (32 or 16 columns)
+  static_assert(kEpiWarps == 8 || kEpiWarps == 16, "8 or 16 epilogue warps");
+  static_assert(!(kTrain && kEpiWarps != 8), "the training forward (masks, TMA tile stores) is written for 8 epilogue warps");
   constexpr int kNumChunks = num_chunks<kFold>();
   constexpr int kSeqLen = layers_per_tile<kFold>();      // accumulator hand-offs per tile and iteration
   extern __shared__ uint8_t smem_raw[];
@@ -222,7 +233,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(sbase + L::acc_full + 8 * t, 1);
-      mbar_init(sbase + L::a_ready + 8 * t, 8 * kCG);     // one arrive per epilogue warp (per CTA)
+      mbar_init(sbase + L::a_ready + 8 * t, kEpiWarps * kCG);   // one arrive per epilogue warp (per CTA)
       mbar_init(sbase + L::pe_ready + 8 * t, 4 * kCG);    // one arrive per PE warp (per CTA)
       mbar_init(sbase + L::pe_free + 8 * t, 1);
     }
@@ -284,7 +295,10 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
               for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t f = kResident ? fill + kb : fill++;
                 const uint32_t stage = f % kStages, round = f / kStages;
-                if (!kResident || t == 0) {
+                // timing experiment (debug instantiation, dbg_layer == -6): never wait for weights after the
+                // first iteration -- how much of the frame is the tensor pipe waiting on the weight ring?
+                const bool skip_w = kTap && args.dbg_layer == -6 && args.dbg_out != nullptr && it > 0;
+                if ((!kResident || t == 0) && !skip_w) {
                   mbar_wait(sbase + L::w_full + 8 * stage, round & 1, wc);
                   if (kPair) mbar_wait(sbase + L::w_peer + 8 * stage, round & 1, wc);
                   tc_fence_after();
@@ -374,7 +388,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     // ================================================================ epilogue ====
     const WaitCtx wc{args.diag, 0x400u};
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int wg = (warp - 8) >> 2;               // column half
+    const int wg = (warp - 8) >> 2;               // column group
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float sig0 = 0.f, sig1 = 0.f;                 // sigma-head partials of tile 0 / tile 1
@@ -406,13 +420,14 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             if (kTrain && args.masks != nullptr && l < 8)
               mask_row = reinterpret_cast<uint8_t*>(args.masks) +
                          mask_img_offset(tile_of(it, t) < args.n_tiles ? tile_of(it, t) : args.n_tiles, l);
+            const bool dbg_half = kTap && args.dbg_layer == -7 && args.dbg_out != nullptr;
             if (l == 7) {
-              const float sig = epilogue_hidden<kEpiReluSigma, kTap, kTrain>(cst, l, d_tmem, hrow, row, wg, tap_row, mask_row);
+              const float sig = epilogue_hidden<kEpiReluSigma, kTap, kTrain, kW>(cst, l, d_tmem, hrow, row, wg, tap_row, mask_row, dbg_half);
               if (t == 0) sig0 = sig; else sig1 = sig;
             } else if (l == 8) {
-              epilogue_hidden<kEpiLinear, kTap, false>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr);
+              epilogue_hidden<kEpiLinear, kTap, false, kW>(cst, l, d_tmem, hrow, row, wg, tap_row, nullptr, dbg_half);
             } else {
-              epilogue_hidden<kEpiRelu, kTap, kTrain>(cst, l, d_tmem, hrow, row, wg, tap_row, mask_row);
+              epilogue_hidden<kEpiRelu, kTap, kTrain, kW>(cst, l, d_tmem, hrow, row, wg, tap_row, mask_row, dbg_half);
             }
             fence_proxy_async_smem();            // my smem writes -> visible to the next layer's UMMA / TMA store
           } else {
@@ -421,9 +436,10 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             const int64_t dray = (pc >> 32) == 0 ? (int64_t)((uint32_t)pc / (uint32_t)args.S) : pc / args.S;
             const float* db = args.dirbias + dray * kViewHidden;
             float r = 0.f, g = 0.f, b = 0.f;
+            constexpr int kViewCols = kViewHidden / kEpiGroups;    // 64 or 32 columns per thread
 #pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-              const int col = wg * 64 + cc * 32;
+            for (int cc = 0; cc < kViewCols / 32; ++cc) {
+              const int col = wg * kViewCols + cc * 32;
               uint32_t v[32];
               tmem_ld32(d_tmem + col, v);
               tmem_wait_ld();
@@ -444,13 +460,18 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
                   *reinterpret_cast<float4*>(args.hv_out + p * kViewHidden + col + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
               }
             }
-            // combine the two column halves through the (now dead) activation tile, then store
+            // combine the column groups through the (now dead) activation tile, then store
             float4* scratch = reinterpret_cast<float4*>(sgen + L::h0 + t * kHBytes);
             const float sig = t == 0 ? sig0 : sig1;
-            if (wg == 1) scratch[row] = make_float4(r, g, b, sig);
-            named_bar_sync(1, 256);
+            if (wg != 0) scratch[(wg - 1) * kTileM + row] = make_float4(r, g, b, sig);
+            named_bar_sync(1, 32 * kEpiWarps);
             if (wg == 0 && p < P) {
-              const float4 o = scratch[row];
+              float4 o = scratch[row];
+#pragma unroll
+              for (int gi = 1; gi < kEpiGroups - 1; ++gi) {
+                const float4 o2 = scratch[gi * kTileM + row];
+                o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w;
+              }
               float4 out;
               out.x = r + o.x + cst.b_rgb[0];
               out.y = g + o.y + cst.b_rgb[1];
@@ -646,10 +667,10 @@ int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t 
   return NWX_OK;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false, bool kFold = false>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false, bool kFold = false, int kEpiWarps = 8>
 static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   using Lay = SmemLayout<kPair, kStages>;
-  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain, kFold>;
+  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain, kFold, kEpiWarps>;
   static bool configured = false;
   if (!configured) {
     NWX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
@@ -668,7 +689,7 @@ static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   args.iters = (int)((tiles + (int64_t)use_units * tiles_per_unit_iter - 1) / ((int64_t)use_units * tiles_per_unit_iter));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kPair ? use_units * 2 : use_units);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(256 + 32 * kEpiWarps);
   cfg.dynamicSmemBytes = Lay::alloc_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

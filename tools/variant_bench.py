@@ -30,7 +30,9 @@ for v in [int(a) for a in sys.argv[1:]] or [1, 2, 3, 4]:
 # timing experiments in the debug instantiation (results are wrong on purpose)
 eng.set_mlp_variant(1)
 dummy = torch.zeros(5 * 4096 * 2, device=dev)
-for mode, name in ((-5, "debug instantiation, normal"), (-3, "no STS in hidden epilogues"), (-4, "no epilogue work")):
+for mode, name in ((-5, "debug instantiation, normal"), (-3, "no STS in hidden epilogues"), (-4, "no epilogue work"),
+                   (-6, "MMA issuer never waits for weights (results wrong on purpose)"),
+                   (-7, "hidden epilogues process half their columns (results wrong on purpose)")):
     eng.debug_tap(mode, dummy)
     for _ in range(2):
         eng.mlp_forward(E.FINE, rays, z)
