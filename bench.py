@@ -164,19 +164,21 @@ def mlp_dram_traffic_per_step():
     """dram__bytes_read.sum + dram__bytes_write.sum of the two mlp_fused_kernel launches of one step,
     from the committed `ncu --set full` capture (profiles/r01_ncu_mlp_full.csv); None if absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_ncu_mlp_full.csv")
+    path = os.path.join(ROOT, "profiles", "r01_ncu_mlp_full_fold.csv")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         rows = list(csv.reader(f))
     hdr, units = rows[0], rows[1]
     total = 0.0
-    for r in rows[2:]:
+    # the capture holds the fine launch (58.98 M points); DRAM traffic is per point (z in, raw out, dirbias), so the
+    # step's two launches (78.64 M points) move 4/3 of it
+    for r in rows[2:3]:
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
             total += float(r[i]) * scale
-    return total
+    return total * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) / (N_SAMPLES + N_IMPORTANCE)
 
 
 def measured_peak_tflops():
@@ -292,7 +294,8 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": mlp_dram_traffic_per_step(),
-                         "traffic_note": "DRAM bytes of the step's two launches, ncu --set full (profiles/r01_ncu_mlp_full.csv); "
+                         "traffic_note": "DRAM bytes of the step's two launches: ncu --set full of the fine launch "
+                                         "(profiles/r01_ncu_mlp_full_fold.csv, 1.32 GB) scaled by points; "
                                          "algorithmic: 20 B/point + 556 B/ray = 1.74 GB",
                          "kernel": "mlp_fused_kernel (2 launches/step)",
                          "peak_source": peak_src, "flop_per_step": mlp_flop, "kernel_ms_per_step": mlp_ms,
