@@ -113,18 +113,26 @@ enum { kEpiRelu = 0, kEpiReluSigma = 1, kEpiLinear = 2 };
 template <int kMode, bool kTap, bool kSave, int W>
 __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, const uint32_t (&v)[W], int col, uint32_t hrow,
                                                int row, float* tap_row, uint8_t* grow /* mask words of (tile, layer) */,
-                                               float& sig) {
+                                               uint64_t& sig2 /* sigma head: (even, odd) column partial sums */) {
   static_assert(W == 32 || W == 16, "chunk of 32 columns (8 epilogue warps) or 16 (16 epilogue warps)");
   static_assert(!kSave || W == 32, "the training masks are one word per 32 columns");
   uint32_t pk[W / 2];
   const bool no_sts = kTap && hrow == 0;          // timing experiment (debug instantiation only)
+  // `col` is warp-uniform (the warp index comes from a shuffle), so biases and head weights are read from the
+  // constant bank through uniform registers (LDCU.128), four columns per load, and used as packed operands
+  const uint4* bias4 = reinterpret_cast<const uint4*>(&cst.bias[l][col]);
+  const uint4* wa4 = reinterpret_cast<const uint4*>(&cst.w_alpha[col]);
 #pragma unroll
   for (int j = 0; j < W; j += 2) {
-    const float a = __uint_as_float(v[j]) + cst.bias[l][col + j];
-    const float b = __uint_as_float(v[j + 1]) + cst.bias[l][col + j + 1];
+    // two columns per instruction: packed fp32x2 add (sm_100 FADD2)
+    const uint4 bq = bias4[j >> 2];
+    const uint64_t bias2 = (j & 2) ? ((uint64_t)bq.z | ((uint64_t)bq.w << 32)) : ((uint64_t)bq.x | ((uint64_t)bq.y << 32));
+    const uint64_t ab = fadd2((uint64_t)v[j] | ((uint64_t)v[j + 1] << 32), bias2);
+    const float a = f32x2_lo(ab), b = f32x2_hi(ab);
     if (kMode == kEpiReluSigma) {                  // sigma head on fp32 relu(h7), nerf_model.py:63
-      sig = fmaf(fmaxf(a, 0.f), cst.w_alpha[col + j], sig);
-      sig = fmaf(fmaxf(b, 0.f), cst.w_alpha[col + j + 1], sig);
+      const uint4 wq = wa4[j >> 2];
+      const uint64_t w2 = (j & 2) ? ((uint64_t)wq.z | ((uint64_t)wq.w << 32)) : ((uint64_t)wq.x | ((uint64_t)wq.y << 32));
+      sig2 = ffma2(f32x2(fmaxf(a, 0.f), fmaxf(b, 0.f)), w2, sig2);
     }
     if (kTap && tap_row) {
       tap_row[col + j] = kMode == kEpiLinear ? a : fmaxf(a, 0.f);
@@ -160,7 +168,7 @@ __device__ __forceinline__ void epilogue_chunk(const MlpConsts& cst, int l, cons
 template <int kMode, bool kTap, bool kSave, int W>
 __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, uint32_t d_tmem, uint32_t hrow,
                                                  int row, int wg, float* tap_row, uint8_t* grow, bool dbg_half = false) {
-  float sig = 0.f;
+  uint64_t sig = 0;                  // (even, odd) column partial sums of the sigma head, fp32 each
   const int col0 = wg * 4 * W;
   uint32_t va[W], vb[W];
   tmem_ld(d_tmem + col0, va);
@@ -170,7 +178,7 @@ __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, ui
   tmem_wait_ld_dep(vb);
   if (kTap && dbg_half) {            // timing experiment: half the epilogue (what twice the epilogue warps would leave per thread)
     epilogue_chunk<kMode, kTap, kSave, W>(cst, l, vb, col0 + W, hrow, row, tap_row, grow, sig);
-    return sig;
+    return f32x2_lo(sig) + f32x2_hi(sig);
   }
   tmem_ld(d_tmem + col0 + 2 * W, va);
   epilogue_chunk<kMode, kTap, kSave, W>(cst, l, vb, col0 + W, hrow, row, tap_row, grow, sig);
@@ -179,7 +187,7 @@ __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, ui
   epilogue_chunk<kMode, kTap, kSave, W>(cst, l, va, col0 + 2 * W, hrow, row, tap_row, grow, sig);
   tmem_wait_ld_dep(vb);
   epilogue_chunk<kMode, kTap, kSave, W>(cst, l, vb, col0 + 3 * W, hrow, row, tap_row, grow, sig);
-  return sig;
+  return f32x2_lo(sig) + f32x2_hi(sig);
 }
 
 template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold, int kEpiWarps>
@@ -211,7 +219,10 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle so that the compiler knows it (and the column group / bias addresses derived
+  // from it) is warp-uniform: the epilogue's biases then come straight from the constant bank through uniform
+  // registers instead of one LDC per pair of columns
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0;
   const int units = kPair ? gridDim.x / 2 : gridDim.x;
   const int unit = kPair ? blockIdx.x / 2 : blockIdx.x;
@@ -435,31 +446,39 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             const int64_t pc = p < P ? p : P - 1;
             const int64_t dray = (pc >> 32) == 0 ? (int64_t)((uint32_t)pc / (uint32_t)args.S) : pc / args.S;
             const float* db = args.dirbias + dray * kViewHidden;
-            float r = 0.f, g = 0.f, b = 0.f;
+            uint64_t r2 = 0, g2 = 0, b2 = 0;     // rgb head partial sums over (even, odd) columns, packed fp32x2
             constexpr int kViewCols = kViewHidden / kEpiGroups;    // 64 or 32 columns per thread
+            auto pair = [](uint32_t lo, uint32_t hi) -> uint64_t { return (uint64_t)lo | ((uint64_t)hi << 32); };
 #pragma unroll 1
             for (int cc = 0; cc < kViewCols / 32; ++cc) {
               const int col = wg * kViewCols + cc * 32;
               uint32_t v[32];
               tmem_ld32(d_tmem + col, v);
               tmem_wait_ld();
+              const uint4* wr4 = reinterpret_cast<const uint4*>(&cst.w_rgb[0][col]);
+              const uint4* wg4 = reinterpret_cast<const uint4*>(&cst.w_rgb[1][col]);
+              const uint4* wb4 = reinterpret_cast<const uint4*>(&cst.w_rgb[2][col]);
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + col + j));
-                float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                const uint4 d4 = __ldg(reinterpret_cast<const uint4*>(db + col + j));
+                const uint4 wr = wr4[j >> 2], wgq = wg4[j >> 2], wb = wb4[j >> 2];
+                float dd[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float hv = fmaxf(__uint_as_float(v[j + q]) + dd[q], 0.f);       // nerf_model.py:68-70
-                  if (kTap && tap_row) tap_row[col + j + q] = hv;
-                  dd[q] = hv;
-                  r = fmaf(hv, cst.w_rgb[0][col + j + q], r);                            // :74
-                  g = fmaf(hv, cst.w_rgb[1][col + j + q], g);
-                  b = fmaf(hv, cst.w_rgb[2][col + j + q], b);
+                for (int q = 0; q < 4; q += 2) {
+                  const uint64_t pre = fadd2(pair(v[j + q], v[j + q + 1]), q ? pair(d4.z, d4.w) : pair(d4.x, d4.y));   // nerf_model.py:68-70
+                  dd[q] = fmaxf(f32x2_lo(pre), 0.f);
+                  dd[q + 1] = fmaxf(f32x2_hi(pre), 0.f);
+                  if (kTap && tap_row) { tap_row[col + j + q] = dd[q]; tap_row[col + j + q + 1] = dd[q + 1]; }
+                  const uint64_t hv2 = f32x2(dd[q], dd[q + 1]);
+                  r2 = ffma2(hv2, q ? pair(wr.z, wr.w) : pair(wr.x, wr.y), r2);                 // :74
+                  g2 = ffma2(hv2, q ? pair(wgq.z, wgq.w) : pair(wgq.x, wgq.y), g2);
+                  b2 = ffma2(hv2, q ? pair(wb.z, wb.w) : pair(wb.x, wb.y), b2);
                 }
                 if (kTrain && args.hv_out != nullptr && p < P)      // post-ReLU views hidden, for the backward
                   *reinterpret_cast<float4*>(args.hv_out + p * kViewHidden + col + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
               }
             }
+            const float r = f32x2_lo(r2) + f32x2_hi(r2), g = f32x2_lo(g2) + f32x2_hi(g2), b = f32x2_lo(b2) + f32x2_hi(b2);
             // combine the column groups through the (now dead) activation tile, then store
             float4* scratch = reinterpret_cast<float4*>(sgen + L::h0 + t * kHBytes);
             const float sig = t == 0 ? sig0 : sig1;

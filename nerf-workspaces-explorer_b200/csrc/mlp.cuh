@@ -28,7 +28,7 @@ __host__ __device__ constexpr uint32_t kblock_offset(int g) {
 }
 
 // fp32 side data of one network, passed to the kernel by value (constant bank).
-struct MlpConsts {
+struct alignas(16) MlpConsts {     // 16-byte aligned: the epilogues read it with 128-bit uniform constant loads
   float bias[9][kHidden];            // _pts_linears.{0..7}.bias, _feature_linear.bias
   float w_alpha[kHidden];            // _alpha_linear.weight
   float w_rgb[3][kViewHidden];       // _rgb_linear.weight

@@ -216,6 +216,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// packed fp32x2 arithmetic (sm_100 FADD2 / FFMA2): two columns per instruction in the epilogues
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+  return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float f32x2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f32x2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

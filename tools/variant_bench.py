@@ -32,7 +32,8 @@ eng.set_mlp_variant(1)
 dummy = torch.zeros(5 * 4096 * 2, device=dev)
 for mode, name in ((-5, "debug instantiation, normal"), (-3, "no STS in hidden epilogues"), (-4, "no epilogue work"),
                    (-6, "MMA issuer never waits for weights (results wrong on purpose)"),
-                   (-7, "hidden epilogues process half their columns (results wrong on purpose)")):
+                   (-7, "hidden epilogues process half their columns (results wrong on purpose)"),
+                   (-8, "epilogues only read TMEM: no ALU work, no smem stores (results wrong on purpose)")):
     eng.debug_tap(mode, dummy)
     for _ in range(2):
         eng.mlp_forward(E.FINE, rays, z)
