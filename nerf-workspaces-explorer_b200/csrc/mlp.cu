@@ -409,6 +409,15 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
         const uint32_t seq = (uint32_t)it * kSeqLen + layer_seq<kFold>(l);
         for (int t = 0; t < 2; ++t) {
           if (lane == 0 && quad == 0) trace(3 + wg, 11, it, l, t);
+          if (l == 9) {
+            // views layer: this row's per-ray term (two 128 B lines of dirbias) is needed the moment the
+            // accumulator is ready -- pull it into L1 while the tensor pipe is still working on it
+            const int64_t pp = tile_of(it, t) * kTileM + row, pq = pp < P ? pp : P - 1;
+            const int64_t ry = (pq >> 32) == 0 ? (int64_t)((uint32_t)pq / (uint32_t)args.S) : pq / args.S;
+            const float* pf = args.dirbias + ry * kViewHidden + wg * (kViewHidden / kEpiGroups);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+            if (kEpiGroups == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 32));
+          }
           mbar_wait(sbase + L::acc_full + 8 * t, seq & 1, wc);   // phase index = seq
           tc_fence_after();
           if (lane == 0 && quad == 0) trace(3 + wg, 12, it, l, t);
@@ -454,7 +463,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
               const int col = wg * kViewCols + cc * 32;
               uint32_t v[32];
               tmem_ld32(d_tmem + col, v);
-              tmem_wait_ld();
+              tmem_wait_ld_dep(v);               // dependency form: the dirbias loads may be scheduled above the wait
               const uint4* wr4 = reinterpret_cast<const uint4*>(&cst.w_rgb[0][col]);
               const uint4* wg4 = reinterpret_cast<const uint4*>(&cst.w_rgb[1][col]);
               const uint4* wb4 = reinterpret_cast<const uint4*>(&cst.w_rgb[2][col]);
