@@ -148,7 +148,8 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0),   // warp-uniform for the compiler
+             lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int units = gridDim.x / 2, unit = blockIdx.x / 2;
   const int64_t P = args.P;
@@ -411,7 +412,8 @@ mlp_bwd_dw_kernel(const __grid_constant__ DwArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0),   // warp-uniform for the compiler
+             lane = threadIdx.x & 31;
   const int64_t n_tiles = args.n_tiles;
   int jidx = 0;
   while (jidx + 1 < kDwJobs && (int)blockIdx.x >= args.job[jidx].cta0 + args.job[jidx].ncta) ++jidx;
