@@ -42,6 +42,8 @@ FLOP_PER_POINT = 1186816                 # 593 408 MAC, unpadded reference shape
 # 63 -> 64: 64*256 + 4*256*256 + 320*256 + 2*256*256 + 256*128 tensor-core MAC + 640 MAC of fp32 heads.
 FLOP_PER_POINT_EXECUTED = 2 * (64 * 256 + 4 * 65536 + 320 * 256 + 2 * 65536 + 256 * 128 + 256 + 384)
 POINTS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)
+WORKLOAD = ("640x480 Replica-shaped frame, 64 coarse + 128 fine samples, one view per GPU, "
+            "rays sharded contiguously across ranks, uint8 pixel tiles all-gathered (NCCL)")
 CPU_SAMPLE_RAYS = 16384                  # two reference inference chunks (yaml inference.chunk = 8192)
 
 
@@ -151,8 +153,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "640x480 view, 64 coarse + 128 fine samples (bounded CPU sample per step)",
-                   "rays_per_step": CPU_SAMPLE_RAYS},
+        "config": {"workload": WORKLOAD, "rays_per_step": CPU_SAMPLE_RAYS, "points_per_ray": POINTS_PER_RAY,
+                   "weights": "random-init reference architecture (seed 0, alpha bias 0.1)",
+                   "sample": "each step renders a bounded 16384-ray strided sample of the frame on the host cores"},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_frame_extrapolated": 1e3 * H * W / value, "gpu_launches": 0,
@@ -281,8 +284,7 @@ def run_gpu_arm(args):
             "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "640x480 Replica-shaped frame, 64 coarse + 128 fine samples, one view per GPU, "
-                                   "rays sharded contiguously across ranks, uint8 pixel tiles all-gathered (NCCL)",
+            "config": {"workload": WORKLOAD,
                        "rays_per_step": rays_per_step, "points_per_ray": POINTS_PER_RAY,
                        "weights": "random-init reference architecture (seed 0, alpha bias 0.1)",
                        "l2": "per-step working set 1.6 GB (raw_fine alone 0.94 GB) >> 126 MB L2; no explicit flush"},
