@@ -186,9 +186,12 @@ int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream);
  * NWX_PARAMS_PER_NET floats in state_dict order; nwx_param_offsets gives the 24 tensor offsets. */
 int nwx_param_offsets(int* offsets24 /* host, 24 ints */);
 
-/* Re-pack one network (bf16 forward images, transposed images for the backward, device-side
- * biases/heads) from its flat master parameters.  Stream-ordered, no host synchronisation; call
- * after every optimiser step.  (nwx_load_weights is the inference-time equivalent.) */
+/* Re-pack one network (bf16 forward images incl. the folded views layer W_view[:, :256] . W_feature,
+ * transposed images for the backward, device-side biases/heads) from its flat master parameters.
+ * Stream-ordered, no host synchronisation; call after every optimiser step.  (nwx_load_weights is the
+ * inference-time equivalent.)  params_flat must stay allocated until the next nwx_train_pack of this
+ * network: the backward reads the fp32 W_view / W_feature / b_feature from it for the chain rule
+ * through the fold (d W_fold -> d W_view, d W_feature, d b_feature). */
 int nwx_train_pack(nwx_ctx* ctx, int which, const float* params_flat, void* stream);
 
 typedef struct nwx_train_io {
