@@ -209,9 +209,18 @@ sample_pdf_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
   }
 }
 
+// One resident wave: the kernel is persistent (warps stride over the rays), and 37 KB of shared memory per block
+// means 6 blocks fit on an SM, not 8 -- a grid of 8 per SM ran 1.33 waves with a third of the machine idle at the end.
+template <bool kFromCoarse>
 static inline unsigned pdf_grid(int64_t N) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sample_pdf_kernel<kFromCoarse>, kPdfWarps * 32, 0) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 4;
+  }
   int64_t blocks = (N + kPdfWarps - 1) / kPdfWarps;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
   return (unsigned)(blocks < cap ? blocks : cap);
 }
 
@@ -223,7 +232,7 @@ int nwx::launch_sample_pdf(const float* z_c, const float* w_c, int Sc, const flo
   NWX_REQUIRE(N >= 0 && Sc >= 11 && Sc <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
   if (N == 0) return NWX_OK;
   NWX_REQUIRE(z_c && w_c && z_samples && (u || u_lin || rng.on));
-  nwx::sample_pdf_kernel<true><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, st>>>(
+  nwx::sample_pdf_kernel<true><<<nwx::pdf_grid<true>(N), nwx::kPdfWarps * 32, 0, st>>>(
       z_c, w_c, Sc, Sc - 1, u, rng, u_lin, n_imp, N, z_samples, z_fine, inds, z_std, nullptr);
   NWX_LAUNCHED();
   return NWX_OK;
@@ -242,7 +251,7 @@ extern "C" int nwx_sample_pdf_bins(const float* bins, const float* weights, int 
   NWX_REQUIRE(N >= 0 && M >= 10 && M <= nwx::kMaxBins && n_imp >= 1 && n_imp <= nwx::kMaxImp);
   if (N == 0) return NWX_OK;
   NWX_REQUIRE(bins && weights && samples && (u || u_lin));
-  nwx::sample_pdf_kernel<false><<<nwx::pdf_grid(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
+  nwx::sample_pdf_kernel<false><<<nwx::pdf_grid<false>(N), nwx::kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
       bins, weights, 0, M, u, nwx::RngSpec{}, u_lin, n_imp, N, samples, nullptr, inds, nullptr, cdf_out);
   NWX_LAUNCHED();
   return NWX_OK;
