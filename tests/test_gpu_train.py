@@ -174,6 +174,17 @@ def test_training_handler_render_methods_vs_reference_golden():
     assert float((a["rgb_fine"] - d["rgb_fine"]).abs().max()) < 0.05                 # one Adam step at lr 5e-4
 
 
+def test_gradients_are_bitwise_reproducible(trainer):
+    """No atomics anywhere in the step (job-major dW partials, per-block head partials, ordered loss sum):
+    the same batch with the same draws gives the same bits, run after run."""
+    g = load_golden("render_train")
+    args = [g[k].to(DEV) for k in ("rays",)] + [g["gt"].float().to(DEV)] + [g[k].to(DEV) for k in ("t_rand", "u", "noise_c", "noise_f")]
+    l1 = trainer.forward_backward(*args).clone(); g1 = trainer.grads.clone()
+    l2 = trainer.forward_backward(*args).clone(); g2 = trainer.grads.clone()
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+    assert bool(torch.isfinite(g1).all()) and float(g1.abs().max()) > 0
+
+
 def test_checkpoint_round_trip_reference_format(tmp_path):
     """Trainer -> reference-format .ckpt -> (a) torch.optim.Adam accepts the optimizer state,
     (b) the inference handler loads it through initialize_models (handler:130-141) and renders with
