@@ -40,8 +40,9 @@ struct alignas(16) MlpConsts {     // 16-byte aligned: the epilogues read it wit
 // The training forward saves every tensor-core operand as the very [128 points x 64 features]
 // bf16 swizzled tile images it builds in shared memory (16 KB each), slot-major:
 //   address(slot, tile, kb) = base + ((slot_kb0(slot) * n_tiles + tile * slot_nkb(slot) + kb) << 14)
-// act slots: 0 = PE (1 K-block), 1..8 = h1..h8 (post-ReLU), 9 = feature output (pre views layer).
-// grad slots (written by the dX kernel): 0 = G_views (2 K-blocks), 1 = d_feature, 2..9 = G8..G1
+// act slots: 0 = PE (1 K-block), 1..8 = h1..h8 (post-ReLU); the feature output (old slot 9) is not
+// materialised since the views layer is folded.
+// grad slots (written by the dX kernel): 0 = G_views (2 K-blocks), 1 = unused (was d_feature), 2..9 = G8..G1
 // (G_l = dL/d(pre-activation of the layer that produced h_l)).
 constexpr int kTileImgBytes = 16384;
 __host__ __device__ constexpr int act_slot_nkb(int s) { return s == 0 ? 1 : 4; }

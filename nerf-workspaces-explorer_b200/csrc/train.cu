@@ -2,21 +2,24 @@
 // nerf/models/nerf_model.py:45-83, as driven by training handler:277-315) and the small kernels
 // of the optimisation step (MSE loss gradient, head gradients, Adam).
 //
-// The training forward (mlp.cu, kTrain) leaves every tensor-core operand in HBM as the same
-// [128 points x 64 features] bf16 swizzled tile images it built in shared memory.  Backward:
+// The training forward (mlp.cu, kTrain; the views layer folded like at inference) leaves every tensor-core
+// operand in HBM as the same [128 points x 64 features] bf16 swizzled tile images it built in shared memory,
+// plus one ReLU' bit word per row and 32-column chunk.  Backward:
 //
 //   dX kernel  (mlp_bwd_dx_kernel): same persistent CTA-pair / two-tiles-in-flight skeleton as the
 //       forward.  Per tile it walks the layers backwards: G_views from the rgb head (CUDA cores),
-//       then 9 tcgen05 GEMM steps  dH_in = G_out . W  with transposed-weight K-block images streamed
-//       by bulk TMA; each epilogue applies the ReLU mask read from the saved activation image
-//       and writes the new G tile to smem (next step's A operand) and to HBM (for dW).
-//   dW kernel  (mlp_bwd_dw_kernel): layer-major.  dW[out,in] = sum_points G[p,out] X[p,in] has the
+//       then 8 tcgen05 GEMM steps  dH_in = G_out . W  with transposed-weight K-block images streamed
+//       by bulk TMA (step 0: the folded views layer); each epilogue applies the ReLU' bit mask and writes
+//       the new G tile to smem (next step's A operand) and to HBM (for dW).
+//   dW kernel  (mlp_bwd_dw_kernel): job-major.  dW[out,in] = sum_points G[p,out] X[p,in] has the
 //       points as the reduction dimension, which is the ROW dimension of the saved images, so both
 //       operands are fed to tcgen05.mma as MN-major tiles (same bytes, a_major = b_major = 1): no
-//       transposes anywhere.  Each CTA accumulates a full dW in TMEM (2 x [128 x 256] fp32) over its
-//       share of the tiles and writes one partial; bias gradients are column sums of the G tiles
-//       taken from shared memory by otherwise idle warps.  A small kernel reduces the partials.
+//       transposes anywhere.  The 10 (G, X) pairs are dealt to the CTAs; each CTA accumulates ONE dW in
+//       TMEM over its share of the tiles and writes one partial; bias gradients are column sums of the
+//       G tiles taken from shared memory by otherwise idle warps.  A small kernel reduces the partials.
+//   fold_sum / fold_grads_*: chain rule from d W_fold back to d W_view[:, :256], d W_feature, d b_feature.
 //   head_{rgb,dir,sigma}_kernel: rgb / sigma heads and the 27 view-direction columns of the views layer (fp32).
+//   No atomics anywhere: gradients and losses are bitwise reproducible.
 #include "mlp_device.cuh"
 
 namespace nwx {

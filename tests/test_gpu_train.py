@@ -188,8 +188,7 @@ def test_gradients_are_bitwise_reproducible(trainer):
 def test_checkpoint_round_trip_reference_format(tmp_path):
     """Trainer -> reference-format .ckpt -> (a) torch.optim.Adam accepts the optimizer state,
     (b) the inference handler loads it through initialize_models (handler:130-141) and renders with
-    exactly the trained weights, (c) a second Trainer resumes on the same trajectory (the head gradients
-    are accumulated with fp32 atomics, so two runs agree to rounding, not bitwise)."""
+    exactly the trained weights, (c) a second Trainer resumes on the same trajectory."""
     import nwx
     eng = nwx.Engine(torch.device(DEV))
     tr = nwx.Trainer(eng, *_nets(), perturb=0.0, raw_noise_std=0.0)
@@ -253,7 +252,7 @@ def test_in_kernel_rng_statistics_and_equivalence():
     for k in want:
         assert torch.equal(a[k], b[k]), k
     assert not torch.equal(a["rgb_fine"], eng.render_rays(rays, want=want)["rgb_fine"])      # the draws matter
-    # and through the trainer: in-kernel draws == injected tensors (gradients to atomics' rounding)
+    # and through the trainer: in-kernel draws == injected tensors (gradients to rounding)
     tr = nwx.Trainer(nwx.Engine(torch.device(DEV)), sd_c, sd_f, seed=seed)
     tr.draws = off
     gt = g["gt"].float().to(DEV)
