@@ -47,6 +47,10 @@ def test_library_is_blackwell_native(nwx_mod):
         assert mnemonic in sass, mnemonic
     assert "UTCHMMA.2CTA" in sass                              # cta_group::2 variant present
     assert not re.search(r"\bHMMA\b", sass)
+    # the MLP epilogue: biases through uniform registers (LDCU) into packed fp32x2 adds (FADD2), packed
+    # bf16 conversion with the ReLU folded in, 128-bit shared-memory stores; TMA tile stores in training
+    for mnemonic in ("LDCU.64", "FADD2", "FFMA2", "F2FP.RELU.BF16.F32.PACK_AB", "STS.128", "UBLKCP.G.S"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_gpu_means_error_not_fallback(nwx_mod):
