@@ -99,6 +99,10 @@ __device__ __forceinline__ float ray_dnorm(const float* __restrict__ rays_d, int
   return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));   // torch.norm, :60
 }
 
+// Forward.  Lane-contiguous layout: lane l owns the K consecutive samples [l*K, l*K + K) of the ray, so the
+// per-sample chain (dist -> alpha -> local transmittance product) is lane-local and ONE fp64 warp scan per ray
+// (over the lanes' products) replaces one scan per 32-sample chunk; the lanes' K x 16 B runs tile the ray's
+// contiguous [S,4] block, so every fetched sector is used (through L1).
 template <int K>
 __global__ void __launch_bounds__(kCompWarps * 32, 4)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
@@ -109,45 +113,50 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const bool noisy = noise != nullptr || rng.on;
+  const int s0 = lane * K;
   int bad = 0;
   for (int64_t ray = warp0; ray < N; ray += nwarps) {
-    // every load of the ray is issued before any math (K float4 + K (+K) scalar loads in flight per
-    // lane); the chunks are then consumed in order, nothing per-sample is kept: 64 registers,
-    // 4 blocks of 8 warps per SM.
-    float zr[K], nz[K];
+    const int64_t base = ray * S;
+    float zr[K + 1], nz[K];
     float4 rw[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int s = j * 32 + lane;
-      const int64_t idx = ray * S + (s < S ? s : S - 1);
-      zr[j] = ldg_stream(z + idx);
-      rw[j] = ldg_stream4(reinterpret_cast<const float4*>(raw) + idx);
-      nz[j] = noise ? ldg_stream(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
+    for (int j = 0; j < K; ++j) {                               // every load of the ray before any math
+      const int s = s0 + j;
+      const int64_t idx = base + (s < S ? s : S - 1);
+      zr[j] = __ldg(z + idx);
+      rw[j] = __ldg(reinterpret_cast<const float4*>(raw) + idx);
+      nz[j] = noise ? __ldg(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
     }
-    const bool noisy = noise != nullptr || rng.on;
+    zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // z of the sample after my last one
     const float dnorm = ray_dnorm(rays_d, d_stride, ray);
-    double carry = 1.0;
+    float alpha[K];
+    double tloc[K];                                             // product of t over my samples before j
+    double p = 1.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int s = s0 + j;
+      float dist = (s >= S - 1) ? 1e10f : __fsub_rn(zr[j + 1], zr[j]);       // :51,:56
+      dist = __fmul_rn(dist, dnorm);                                        // :60
+      const float sg = noisy ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
+      float a = __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg, 0.0f), dist)));   // :49
+      float t = __fadd_rn(__fsub_rn(1.0f, a), 1e-10f);                      // :75
+      if (s >= S) { a = 0.0f; t = 1.0f; }                                   // padding samples: neutral
+      alpha[j] = a;
+      tloc[j] = p;
+      p *= (double)t;
+    }
+    const double incl = warp_incl_prod(p, lane);                // :75 cumprod (exclusive), fp64 like torch
+    double excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0;
     float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      const int s = j * 32 + lane;
-      float znext = __shfl_down_sync(kFull, zr[j], 1);
-      const float zhead = __shfl_sync(kFull, zr[(j + 1 < K) ? j + 1 : j], 0);
-      if (lane == 31) znext = zhead;
-      float dist = (s >= S - 1) ? 1e10f : __fsub_rn(znext, zr[j]);          // :51,:56
-      dist = __fmul_rn(dist, dnorm);                                        // :60
-      const float sg = noisy ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
-      float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg, 0.0f), dist)));   // :49
-      float t = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);                   // :75
-      if (s >= S) { alpha = 0.0f; t = 1.0f; }                               // padding lanes: neutral
-      const double incl = warp_incl_prod((double)t, lane);
-      double excl = __shfl_up_sync(kFull, incl, 1);
-      if (lane == 0) excl = 1.0;
-      const float T = (float)(carry * excl);                                // :75 (cumprod, exclusive)
-      carry *= __shfl_sync(kFull, incl, 31);
-      const float w = __fmul_rn(alpha, T);
+      const int s = s0 + j;
+      const float T = (float)(excl * tloc[j]);
+      const float w = __fmul_rn(alpha[j], T);
       if (s < S) {
-        if (weights) weights[ray * S + s] = w;
+        if (weights) weights[base + s] = w;
         a_r += __fmul_rn(w, sigmoidf_fast(rw[j].x));                        // :62,:84
         a_g += __fmul_rn(w, sigmoidf_fast(rw[j].y));
         a_b += __fmul_rn(w, sigmoidf_fast(rw[j].z));
