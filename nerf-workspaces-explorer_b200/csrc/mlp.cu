@@ -655,41 +655,51 @@ int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
 __global__ void __launch_bounds__(kViewHidden)
 dirbias_kernel(const float* __restrict__ dirs, int stride, int64_t n, int pre_embedded,
                const float* __restrict__ wdir_t, const float* __restrict__ bview, float* __restrict__ out) {
-  constexpr int kRays = 8;
-  __shared__ float pe[kRays][kPeDir + 1];
+  // thread = output column j with its 27 weights in registers; 32 rays per block, their embeddings in shared
+  // memory as 7 float4 each (27 + one zero), read as broadcast LDS.128: 7 loads + 27 FMAs per output.
+  constexpr int kRays = 32, kQ = (kPeDir + 3) / 4;
+  __shared__ float4 pe4[kRays][kQ];
+  float* pe = reinterpret_cast<float*>(&pe4[0][0]);
   const int64_t base = (int64_t)blockIdx.x * kRays;
-  for (int e = threadIdx.x; e < kRays * kPeDir; e += blockDim.x) {
-    const int r = e / kPeDir, i = e - r * kPeDir;
+  for (int e = threadIdx.x; e < kRays * 4 * kQ; e += blockDim.x) {
+    const int r = e / (4 * kQ), i = e - r * (4 * kQ);
     const int64_t ray = base + r < n ? base + r : n - 1;
-    float v;
-    if (pre_embedded || i < 3) v = __ldg(dirs + ray * stride + i);
-    else {
-      const int k = (i - 3) / 6, w = (i - 3) % 6, a = w % 3;
-      const float x = __ldg(dirs + ray * stride + a) * (float)(1 << k);
-      v = (w < 3) ? sinf(x) : cosf(x);
+    float v = 0.0f;
+    if (i < kPeDir) {
+      if (pre_embedded || i < 3) v = __ldg(dirs + ray * stride + i);
+      else {
+        const int k = (i - 3) / 6, w = (i - 3) % 6, a = w % 3;
+        const float x = __ldg(dirs + ray * stride + a) * (float)(1 << k);
+        v = (w < 3) ? sinf(x) : cosf(x);
+      }
     }
-    pe[r][i] = v;
+    pe[e] = v;
   }
-  __syncthreads();
   const int j = threadIdx.x;
-  float acc[kRays];
+  float w[4 * kQ];
+#pragma unroll
+  for (int i = 0; i < 4 * kQ; ++i) w[i] = i < kPeDir ? __ldg(wdir_t + i * kViewHidden + j) : 0.0f;
   const float b = __ldg(bview + j);
+  __syncthreads();
+#pragma unroll 4
+  for (int r = 0; r < kRays; ++r) {
+    float acc = b;                                  // same summation order as before: i = 0 .. 26
 #pragma unroll
-  for (int r = 0; r < kRays; ++r) acc[r] = b;
-  for (int i = 0; i < kPeDir; ++i) {
-    const float w = __ldg(wdir_t + i * kViewHidden + j);
-#pragma unroll
-    for (int r = 0; r < kRays; ++r) acc[r] = fmaf(w, pe[r][i], acc[r]);
+    for (int q = 0; q < kQ; ++q) {
+      const float4 p = pe4[r][q];
+      acc = fmaf(w[4 * q + 0], p.x, acc);
+      acc = fmaf(w[4 * q + 1], p.y, acc);
+      acc = fmaf(w[4 * q + 2], p.z, acc);
+      if (4 * q + 3 < kPeDir) acc = fmaf(w[4 * q + 3], p.w, acc);
+    }
+    if (base + r < n) out[(base + r) * kViewHidden + j] = acc;
   }
-#pragma unroll
-  for (int r = 0; r < kRays; ++r)
-    if (base + r < n) out[(base + r) * kViewHidden + j] = acc[r];
 }
 
 int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, bool fold,
                    float* out, cudaStream_t st) {
   if (n == 0) return NWX_OK;
-  dirbias_kernel<<<(unsigned)((n + 7) / 8), kViewHidden, 0, st>>>(dirs, stride, n, pre_embedded ? 1 : 0, net.wdir_t,
+  dirbias_kernel<<<(unsigned)((n + 31) / 32), kViewHidden, 0, st>>>(dirs, stride, n, pre_embedded ? 1 : 0, net.wdir_t,
                                                                  fold ? net.bview_fold : net.bview, out);
   NWX_LAUNCHED();
   return NWX_OK;
