@@ -155,13 +155,13 @@ typedef struct nwx_render_opts {
   int rng_u;                 /* != 0 and u == NULL: random importance uniforms (else deterministic) */
 } nwx_render_opts;
 
-typedef struct nwx_render_out {       /* any pointer may be NULL = not wanted, except rgb_fine */
+typedef struct nwx_render_out {       /* any pointer may be NULL = not wanted; one of rgb_fine / rgb8_fine is required */
   float *rgb_coarse, *disp_coarse, *acc_coarse, *depth_coarse, *raw_coarse;
   float *rgb_fine, *disp_fine, *acc_fine, *depth_fine, *raw_fine, *z_std;
   float *z_vals_coarse, *weights_coarse, *z_samples, *z_vals_fine, *weights_fine;
   int64_t* inds;
   int32_t* flags;
-  uint8_t* rgb8_fine;                 /* to8b(rgb_fine) (model_utils.py:9), [N,3] */
+  uint8_t* rgb8_fine;                 /* to8b(rgb_fine) (model_utils.py:9), [N,3]; written by the compositing kernel itself */
 } nwx_render_out;
 
 /* Reserve the context's scratch for chunks of up to max_rays rays (otherwise grown on demand,
@@ -202,7 +202,20 @@ typedef struct nwx_train_io {
   double* loss;            /* out: [2] = mse(rgb_coarse, gt), mse(rgb_fine, gt) (handler:291-298) */
   float* rgb_coarse;       /* optional out [N,3]                                                */
   float* rgb_fine;         /* optional out [N,3]                                                */
+  void* ev_coarse_done;    /* optional cudaEvent_t, recorded on `stream` as soon as grad_coarse is final
+                              (before the fine network's backward is enqueued): a data-parallel caller
+                              all-reduces the coarse gradients on a side stream underneath it */
 } nwx_train_io;
+
+/* _sample_training_data (training handler:341-370) on the device: ONE random image of the bank and n random
+ * pixels of it (with replacement) from the library's counter-based generator (rng_stream 4: image index,
+ * element 0; rng_stream 5: pixel index of sample r, element r), then the gather.  rays_bank: [num_img, num_ray,
+ * ray_dim] (what initialize_rays builds, :243-263); rgb_bank: [num_img, num_ray, 3]; rays_out: [n, ray_dim];
+ * gt_out: [n,3]; idx_out (may be NULL): int64 [1 + n] = the image index, then the n pixel indices.  No host
+ * synchronisation (the reference draws on the CPU and fancy-indexes). */
+int nwx_sample_training_batch(const float* rays_bank, const float* rgb_bank, int num_img, int64_t num_ray,
+                              int ray_dim, int64_t n, uint64_t seed, uint64_t offset, float* rays_out,
+                              float* gt_out, int64_t* idx_out, void* stream);
 
 /* Forward in training mode (jitter t_rand, noise, random u from opts; training handler:534-618),
  * loss = mse(rgb_coarse) + mse(rgb_fine), backward to both networks' parameters.  What
@@ -217,7 +230,7 @@ int nwx_adam_step(float* params, const float* grads, float* m, float* v, int64_t
 
 /* Per-stage device timing of nwx_render_rays (CUDA events on the caller's stream).  Stage order:
  * coarse_z, dirbias(coarse), mlp(coarse), composite(coarse), sample_pdf, dirbias(fine), mlp(fine),
- * composite(fine)+to8b.  nwx_ctx_stage_ms waits for the last recorded call and fills
+ * composite(fine, incl. the uint8 pixels).  nwx_ctx_stage_ms waits for the last recorded call and fills
  * ms_out[NWX_NUM_STAGES] (host). */
 #define NWX_NUM_STAGES 8
 int nwx_ctx_set_profiling(nwx_ctx* ctx, int on);
@@ -233,9 +246,13 @@ int64_t nwx_launch_count(void);
 int nwx_set_mlp_variant(nwx_ctx* ctx, int variant);
 /* Diagnostics: tap the post-activation fp32 output of tensor-core layer `layer` (0..9) of
  * subsequent MLP launches into out [P,256] (NULL = off); register a host-mapped uint32[4] that
- * a timed-out barrier wait fills before the kernel traps instead of hanging. */
+ * a barrier wait that exceeds its wall-clock bound (10 s) fills before the kernel traps instead of hanging. */
 int nwx_debug_tap(nwx_ctx* ctx, int layer, float* out);
 int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped);
+/* The 4 diagnostic words (0xDEADxxxx | waiter code, block, barrier, parity) of the last aborted wait; zeros
+ * if none.  Every context owns such a host-mapped word from creation (nwx_debug_diag(ctx, NULL) restores
+ * it), so the cause of a trap is readable even though the CUDA context is unusable afterwards. */
+int nwx_ctx_last_diag(nwx_ctx* ctx, uint32_t* out4 /* host */);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,13 @@
 // K4: alpha compositing (raw2outputs, reference nerf/models/model_utils.py:33-100) and its
-// analytic backward.  One warp per ray; sample s of a ray lives in lane s%32, chunk s/32, so
-// every global access is a fully coalesced 128 B (z, weights) or 512 B (raw float4) warp
-// transaction.  The exclusive transmittance product is a warp scan per 32-sample chunk with a
-// running carry.  HBM-bound: 20 B read (+4 noise) and 4 B written per sample, 28 B per ray.
+// analytic backward.  One warp per ray.
+//   forward : lane l owns the K = ceil(S/32) CONSECUTIVE samples [l*K, l*K+K) of the ray, so the per-sample
+//             chain (distance -> alpha -> local transmittance product) is lane-local and ONE fp64 warp scan per
+//             ray (over the lanes' products) replaces a scan per 32-sample chunk; the lanes' K x 16 B runs tile
+//             the ray's contiguous [S,4] block, so every fetched sector is used.  The uint8 image
+//             (to8b_np, model_utils.py:9) is written by the same lane that writes rgb: no extra launch.
+//   backward: sample s lives in lane s%32, chunk s/32 (coalesced 128 B / 512 B warp transactions), one warp
+//             scan per 32-sample chunk with a running carry.
+// HBM-bound on paper: 20 B read (+4 noise) and 4 B written per sample, 28 B per ray.
 //
 // Numerics follow torch-CPU op for op (no FMA contraction; expf/division correctly rounded
 // variants).  torch.cumprod accumulates fp32 input in DOUBLE and rounds every output
@@ -41,6 +46,12 @@ __device__ __forceinline__ float sigmoidf_rn(float x) {        // torch.sigmoid:
 // carry the 1e-3 tolerance of the bf16 MLP; the weights (alpha, transmittance), which decide the
 // importance-sampling indices, keep the exact op-for-op arithmetic.  The backward keeps sigmoidf_rn.
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// numpy (255 * clip(x, 0, 1)).astype(uint8): fp32 multiply, truncation; NaN -> 0  (model_utils.py:9)
+__device__ __forceinline__ uint8_t to8b_one(float v) {
+  v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+  return (uint8_t)(int)__fmul_rn(255.0f, v);
+}
 
 struct RaySample {
   float c[3];     // sigmoid(raw rgb)
@@ -109,7 +120,7 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
                      const RngSpec rng, int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
                      float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
-                     int32_t* __restrict__ flags) {
+                     int32_t* __restrict__ flags, uint8_t* __restrict__ rgb8) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
@@ -173,7 +184,10 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         const float bg = __fsub_rn(1.0f, a_w);
         a_r = __fadd_rn(a_r, bg); a_g = __fadd_rn(a_g, bg); a_b = __fadd_rn(a_b, bg);
       }
-      rgb[ray * 3 + 0] = a_r; rgb[ray * 3 + 1] = a_g; rgb[ray * 3 + 2] = a_b;
+      if (rgb) { rgb[ray * 3 + 0] = a_r; rgb[ray * 3 + 1] = a_g; rgb[ray * 3 + 2] = a_b; }
+      if (rgb8) {                                                         // to8b_np, model_utils.py:9
+        rgb8[ray * 3 + 0] = to8b_one(a_r); rgb8[ray * 3 + 1] = to8b_one(a_g); rgb8[ray * 3 + 2] = to8b_one(a_b);
+      }
       if (disp) disp[ray] = dspv;
       if (acc) acc[ray] = a_w;
       if (depth) depth[ray] = a_d;
@@ -265,12 +279,12 @@ static inline unsigned comp_grid(int64_t N) {
 
 int nwx::launch_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
                               const RngSpec& rng, int64_t N, int S, int white_bkgd, float* rgb, float* disp, float* acc,
-                              float* depth, float* weights, int32_t* flags, cudaStream_t st) {
+                              float* depth, float* weights, int32_t* flags, cudaStream_t st, uint8_t* rgb8) {
   NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
   if (N == 0) return NWX_OK;
-  NWX_REQUIRE(raw && z && rays_d && rgb);
+  NWX_REQUIRE(raw && z && rays_d && (rgb || rgb8));
   NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
-                        raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags)));
+                        raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8)));
   NWX_LAUNCHED();
   return NWX_OK;
 }
@@ -291,8 +305,9 @@ extern "C" int nwx_composite_fwd(const float* raw, const float* z, const float* 
                                  const float* noise, int64_t N, int S, int white_bkgd, float* rgb,
                                  float* disp, float* acc, float* depth, float* weights, int32_t* flags,
                                  void* stream) {
+  NWX_REQUIRE(rgb || N == 0);
   return nwx::launch_composite_fwd(raw, z, rays_d, d_stride, noise, nwx::RngSpec{}, N, S, white_bkgd, rgb, disp, acc,
-                                   depth, weights, flags, (cudaStream_t)stream);
+                                   depth, weights, flags, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int nwx_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,

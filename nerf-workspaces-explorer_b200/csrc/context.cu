@@ -3,12 +3,13 @@
 // nerf/training/nerf_replica_training_handler.py:534-618).
 //
 // The reference walks a frame in 38 Python ray chunks x 64 network chunks, with 22 host syncs
-// per chunk.  Here one chunk of any size is 7 kernel launches on one
+// per chunk.  Here one chunk of any size is 8 kernel launches on one
 // stream, no host synchronisation, nothing per-point materialised except raw [N,S,4]:
 //   coarse_z -> dirbias(coarse) -> MLP(coarse) -> composite -> sample_pdf+merge
-//            -> dirbias(fine)   -> MLP(fine)   -> composite (+ to8b)
+//            -> dirbias(fine)   -> MLP(fine)   -> composite (writes rgb and/or the uint8 pixels)
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "mlp.cuh"
@@ -24,7 +25,8 @@ struct nwx_ctx {
   size_t scratch_floats = 0;
   float* dbg_out = nullptr;      // optional tap target set by nwx_debug_tap
   int dbg_layer = -1;
-  uint32_t* diag = nullptr;      // optional host-mapped diagnostics
+  uint32_t* diag = nullptr;      // host-mapped diagnostics the kernels write before aborting (own_diag unless overridden)
+  uint32_t* own_diag = nullptr;  // 4 words of mapped pinned host memory, allocated with the context
   // optional per-stage device timing of nwx_render_rays (bench.py: roofline of the dominant kernel)
   // training scratch (activation / gradient tile images, dW partials, ...), grown on demand
   uint8_t* tscratch = nullptr;
@@ -110,6 +112,14 @@ extern "C" int nwx_ctx_create(int device, nwx_ctx** out) {
   nwx_ctx* c = new (std::nothrow) nwx_ctx();
   if (!c) return NWX_E_INVALID;
   c->device = device;
+  // always-on diagnostics: survives a poisoned context because it lives in mapped host memory
+  if (cudaHostAlloc(reinterpret_cast<void**>(&c->own_diag), 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess) {
+    memset(c->own_diag, 0, 4 * sizeof(uint32_t));
+    c->diag = c->own_diag;
+  } else {
+    (void)cudaGetLastError();
+    c->own_diag = nullptr;
+  }
   *out = c;
   return NWX_OK;
 }
@@ -133,6 +143,7 @@ extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
   }
   for (auto e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->own_diag) cudaFreeHost(ctx->own_diag);
   delete ctx;
   return NWX_OK;
 }
@@ -158,7 +169,12 @@ extern "C" int nwx_debug_tap(nwx_ctx* ctx, int layer, float* out) {
 }
 extern "C" int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped) {
   NWX_REQUIRE(ctx);
-  ctx->diag = host_mapped;
+  ctx->diag = host_mapped ? host_mapped : ctx->own_diag;
+  return NWX_OK;
+}
+extern "C" int nwx_ctx_last_diag(nwx_ctx* ctx, uint32_t* out4) {
+  NWX_REQUIRE(ctx && out4);
+  for (int i = 0; i < 4; ++i) out4[i] = ctx->diag ? ((volatile uint32_t*)ctx->diag)[i] : 0u;
   return NWX_OK;
 }
 
@@ -238,7 +254,7 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
                                const nwx_render_out* out, void* stream) {
   NWX_REQUIRE(ctx && o && out && N >= 0);
   if (N == 0) return NWX_OK;
-  NWX_REQUIRE(rays && out->rgb_fine);
+  NWX_REQUIRE(rays && (out->rgb_fine || out->rgb8_fine));
   NWX_REQUIRE(o->n_samples >= 11 && o->n_samples <= 128 && o->n_importance >= 1 && o->n_importance <= 128);
   NWX_REQUIRE(o->ray_dim >= NWX_RAY_DIM && o->t_vals && (o->u || o->u_lin || o->rng_u));
   if (N == 0) return NWX_OK;
@@ -284,8 +300,8 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
                     prof ? ctx->ev[6] : nullptr))) return rc;
   if ((rc = mark(7))) return rc;
   if ((rc = nwx::launch_composite_fwd(raw_f, z_f, rays + 3, rd, o->noise_fine, rnf, N, Sf, o->white_bkgd, out->rgb_fine,
-                                      out->disp_fine, out->acc_fine, out->depth_fine, out->weights_fine, out->flags, st))) return rc;
-  if (out->rgb8_fine && (rc = nwx_to8b(out->rgb_fine, N * 3, out->rgb8_fine, st))) return rc;
+                                      out->disp_fine, out->acc_fine, out->depth_fine, out->weights_fine, out->flags, st,
+                                      out->rgb8_fine))) return rc;
   if ((rc = mark(8))) return rc;
   ctx->ev_recorded = prof;
   return NWX_OK;
@@ -314,6 +330,20 @@ extern "C" int nwx_adam_step(float* params, const float* grads, float* m, float*
 }
 
 namespace {
+// The training kernels read biases / heads from process-global __constant__ banks (mlp.cu c_fwd_train_consts,
+// train.cu c_train_consts) that every nwx_train_fwd_bwd refreshes on its own stream.  Two contexts (or one
+// context on two streams) training on the same device would race on them, so consecutive training calls on
+// a device are chained: a call that is not on the previous call's (ctx, stream) first waits -- on the device,
+// no host synchronisation -- for the event the previous call recorded behind its last kernel.  The host-side
+// mutex keeps two host threads from interleaving their enqueues.
+struct TrainGate {
+  std::mutex mu;
+  cudaEvent_t done = nullptr;
+  const nwx_ctx* owner = nullptr;
+  cudaStream_t stream = nullptr;
+};
+TrainGate g_train_gate[nwx::kMaxDevices];
+
 struct TrainPlan {
   size_t acts_c, acts_f, masks_c, masks_f, gimg, head_partial, fold, hv_c, hv_f, d_raw_c, d_raw_f, pe_dir, d_rgb_c, d_rgb_f, rgb_c, rgb_f, total;
 };
@@ -351,6 +381,16 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
   for (int w = 0; w < 2; ++w)
     if (!ctx->net[w].loaded || !ctx->net[w].gconsts || !ctx->net[w].wimg_t) return NWX_E_NO_WEIGHTS;   // nwx_train_pack first
   auto st = (cudaStream_t)stream;
+  TrainGate& gate = g_train_gate[ctx->device >= 0 && ctx->device < nwx::kMaxDevices ? ctx->device : 0];
+  std::lock_guard<std::mutex> gate_lock(gate.mu);
+  if (gate.owner && (gate.owner != ctx || gate.stream != st)) NWX_CUDA_TRY(cudaStreamWaitEvent(st, gate.done, 0));
+  struct GateRelease {       // record "this call's kernels are done" on every exit path after the wait
+    TrainGate& g; const nwx_ctx* c; cudaStream_t s;
+    ~GateRelease() {
+      if (!g.done && cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming) != cudaSuccess) { g.done = nullptr; return; }
+      if (cudaEventRecord(g.done, s) == cudaSuccess) { g.owner = c; g.stream = s; }
+    }
+  } gate_release{gate, ctx, st};
   const int Sc = o->n_samples, Ni = o->n_importance, Sf = Sc + Ni, rd = o->ray_dim;
   const ScratchPlan pl = plan_scratch(N, Sc, Ni);
   int rc = ensure_scratch(ctx, pl.total);
@@ -430,6 +470,8 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     b.pe_dir = pe_dir; b.grad = grads[w]; b.diag = ctx->diag; b.P = N * S[w]; b.S = S[w]; b.max_partials = ctx->n_partials;
     b.which = w;
     if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st))) return rc;
+    // data-parallel callers all-reduce the coarse network's gradients underneath the fine network's backward
+    if (w == 0 && io->ev_coarse_done) NWX_CUDA_TRY(cudaEventRecord((cudaEvent_t)io->ev_coarse_done, st));
   }
   return NWX_OK;
 }

@@ -709,10 +709,11 @@ template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = fals
 static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
   using Lay = SmemLayout<kPair, kStages>;
   auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain, kFold, kEpiWarps>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;                 // the attribute is per device
+  const int dev = current_device();
+  if (configured.need(dev)) {
     NWX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
-    configured = true;
+    configured.done(dev);
   }
   const int64_t tiles = (args.P + kTileM - 1) / kTileM;
   args.n_tiles = tiles;

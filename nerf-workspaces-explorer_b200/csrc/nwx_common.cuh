@@ -53,23 +53,36 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
   return r;
 }
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+// SM count of the CURRENT device (a process may drive several GPUs)
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
+}
+// cudaFuncSetAttribute is per device: one flag per (kernel, device) instead of one per process
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> dev) & 1ull) == 0; }
+  void done(int dev) { mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 // Internal launchers with an optional in-kernel random source (rng.on) in place of the tensors
 int launch_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const float* t_vals, const float* t_rand,
                     const RngSpec& rng, float* z_out, cudaStream_t st);
 int launch_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
                          const RngSpec& rng, int64_t N, int S, int white_bkgd, float* rgb, float* disp, float* acc,
-                         float* depth, float* weights, int32_t* flags, cudaStream_t st);
+                         float* depth, float* weights, int32_t* flags, cudaStream_t st, uint8_t* rgb8 = nullptr);
 int launch_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
                          const RngSpec& rng, const float* d_rgb, int64_t N, int S, int white_bkgd, float* d_raw,
                          cudaStream_t st);

@@ -191,6 +191,55 @@ extern "C" int nwx_rng_fill(int kind, uint64_t seed, uint64_t offset, uint32_t r
   return NWX_OK;
 }
 
+// _sample_training_data (training handler:341-370) on the device: ONE random image of the bank and n pixel
+// indices with replacement, then the gather of the sampled rays and ground-truth pixels.  Thread = one output
+// float (coalesced writes); every thread of a ray re-derives the ray's pixel index from the counter-based
+// generator (stream 5, element = sample number), the image index is element 0 of stream 4.
+namespace nwx {
+__device__ __forceinline__ uint32_t rng_below(const RngSpec& r, uint64_t idx, uint32_t n) {
+  uint32_t x[4];
+  philox4x32_10(r.seed, r.offset, r.stream, idx, x);
+  return (uint32_t)(((uint64_t)x[0] * (uint64_t)n) >> 32);      // uniform in [0, n)
+}
+__global__ void __launch_bounds__(256)
+sample_batch_kernel(const float* __restrict__ rays_bank, const float* __restrict__ rgb_bank, int num_img, uint32_t num_ray,
+                    int ray_dim, int64_t n, RngSpec rng_img, RngSpec rng_pix, float* __restrict__ rays_out,
+                    float* __restrict__ gt_out, int64_t* __restrict__ idx_out) {
+  const int width = ray_dim + 3;
+  const int64_t total = n * width, stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t img = rng_below(rng_img, 0, (uint32_t)num_img);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / width;
+    const int c = (int)(i - r * width);
+    const int64_t pix = rng_below(rng_pix, (uint64_t)r, num_ray);
+    const int64_t src = img * num_ray + pix;
+    if (c < ray_dim) rays_out[r * ray_dim + c] = __ldg(rays_bank + src * ray_dim + c);
+    else gt_out[r * 3 + (c - ray_dim)] = __ldg(rgb_bank + src * 3 + (c - ray_dim));
+    if (idx_out && c == 0) {
+      idx_out[1 + r] = pix;
+      if (r == 0) idx_out[0] = img;
+    }
+  }
+}
+}  // namespace nwx
+
+extern "C" int nwx_sample_training_batch(const float* rays_bank, const float* rgb_bank, int num_img, int64_t num_ray,
+                                         int ray_dim, int64_t n, uint64_t seed, uint64_t offset, float* rays_out,
+                                         float* gt_out, int64_t* idx_out, void* stream) {
+  NWX_REQUIRE(num_img >= 1 && num_ray >= 1 && num_ray <= 0xFFFFFFFFll && ray_dim >= 8 && n >= 0);
+  if (n == 0) return NWX_OK;
+  NWX_REQUIRE(rays_bank && rgb_bank && rays_out && gt_out);
+  nwx::RngSpec ri, rp;
+  ri.seed = rp.seed = seed; ri.offset = rp.offset = offset; ri.stream = 4; rp.stream = 5; ri.on = rp.on = 1;
+  int64_t blocks = (n * (ray_dim + 3) + 255) / 256;
+  const int64_t cap = (int64_t)nwx::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  nwx::sample_batch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      rays_bank, rgb_bank, num_img, (uint32_t)num_ray, ray_dim, n, ri, rp, rays_out, gt_out, idx_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
 extern "C" int nwx_to8b(const float* x, int64_t n, uint8_t* out, void* stream) {
   NWX_REQUIRE(n >= 0);
   if (n == 0) return NWX_OK;

@@ -948,10 +948,11 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
   // ---- dX ----
   {
     using Lay = SmemLayout<true, 4>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;               // the attribute is per device
+    const int dev = current_device();
+    if (configured.need(dev)) {
       NWX_CUDA_TRY(cudaFuncSetAttribute(mlp_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::alloc_bytes));
-      configured = true;
+      configured.done(dev);
     }
     DxArgs d{};
     d.d_raw = a.d_raw; d.hv = a.hv; d.acts = a.acts; d.masks = a.masks; d.grads = a.gimg; d.wimg_t = net.wimg_t; d.gconsts = net.gconsts;
@@ -972,10 +973,11 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
   // ---- dW ----
   int grid = 0;
   {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    if (configured.need(dev)) {
       NWX_CUDA_TRY(cudaFuncSetAttribute(mlp_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DwSmem::alloc_bytes));
-      configured = true;
+      configured.done(dev);
     }
     DwArgs w{};
     w.acts = a.acts; w.grads = a.gimg; w.partial = a.partial; w.diag = a.diag; w.n_tiles = tiles;

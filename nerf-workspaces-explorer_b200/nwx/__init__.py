@@ -17,6 +17,7 @@ from .inference import NeRFReplicaInferenceHandler                         # noq
 from .models import (Embedding, NeRFModel, img2mse, mse2psnr, raw2outputs, run_network,   # noqa: F401
                      to8b, to8b_np)
 from .rays import create_rays, sample_pdf                                  # noqa: F401
+from .reference_patch import patch_reference, unpatch_reference            # noqa: F401
 from .training import NeRFReplicaTrainingHandler, Trainer                  # noqa: F401
 
 from .workspace import (OfficeBelgradeWorkspace, OfficeGeneveWorkspace, OfficeNewYorkWorkspace,   # noqa: F401

@@ -37,7 +37,7 @@ class RenderOut(C.Structure):
 
 class TrainIO(C.Structure):
     _fields_ = [(name, _vp) for name in ("rays", "gt_rgb", "grad_coarse", "grad_fine", "loss", "rgb_coarse",
-                                         "rgb_fine")]
+                                         "rgb_fine", "ev_coarse_done")]
 
 
 # name -> (restype, argtypes); mirrors include/nwx.h one to one
@@ -71,6 +71,8 @@ PROTOTYPES = {
     "nwx_set_mlp_variant": (_i, [_vp, _i]),
     "nwx_debug_tap": (_i, [_vp, _i, _vp]),
     "nwx_debug_diag": (_i, [_vp, _vp]),
+    "nwx_ctx_last_diag": (_i, [_vp, C.POINTER(C.c_uint32)]),
+    "nwx_sample_training_batch": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
 }
 
 

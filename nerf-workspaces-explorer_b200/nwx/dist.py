@@ -46,21 +46,17 @@ def render_sharded(total_rays: int, render_range: Callable[[int, int], torch.Ten
     return gather_tiles(render_range(start, count), total_rays, group)
 
 
-def render_poses_sharded(handler, c2w: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """[B,4,4] poses -> uint8 [B,H,W,3] on every rank, each rank rendering 1/world of the B*H*W rays."""
+def render_poses_sharded(handler, c2w: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                         to_host: bool = False):
+    """[B,4,4] poses -> uint8 [B,H,W,3] on every rank, each rank rendering 1/world of the B*H*W rays (row tiles
+    of the frame when B == 1) and one all-gather of the uint8 tiles.  to_host=True returns the frames as a host
+    array through the handler's pinned read-back buffer (what render_poses returns on one GPU)."""
     eng = handler.engine
     H, W = handler._img_h, handler._img_w
-    c2w_dev = c2w.to(eng.device, dtype=torch.float32)
-
-    def render_range(start: int, count: int) -> torch.Tensor:
-        rgb8 = torch.empty((count, 3), device=eng.device, dtype=torch.uint8)
-        step = handler.max_rays_per_launch
-        for s in range(0, count, step):
-            n = min(step, count - s)
-            rays = eng.raygen(c2w_dev, H, W, handler._fx, handler._fy, handler._cx, handler._cy,
-                              handler._depth_close_bound, handler._depth_far_bound, True, ray0=start + s, nrays=n)
-            eng.render_rays(rays, handler._n_samples, handler._n_importance, handler._white_bkgd,
-                            want=("rgb8_fine",), out={"rgb8_fine": rgb8[s:s + n]})
-        return rgb8
-
-    return render_sharded(c2w.shape[0] * H * W, render_range, group).view(c2w.shape[0], H, W, 3)
+    B = c2w.shape[0]
+    c2w_dev = c2w.to(eng.device, dtype=torch.float32, non_blocking=True)
+    with torch.no_grad():
+        full = render_sharded(B * H * W, lambda start, count: handler.render_rays_u8(c2w_dev, start, count), group)
+    if to_host:
+        return handler.frames_to_host(full, B)
+    return full.view(B, H, W, 3)

@@ -155,6 +155,13 @@ class Engine:
     def debug_diag(self, pinned: Optional[torch.Tensor]) -> None:
         check(self._lib.nwx_debug_diag(self._ctx, _ptr(pinned)), "nwx_debug_diag")
 
+    def last_diag(self) -> Tuple[int, int, int, int]:
+        """(0xDEADxxxx | waiter, block, barrier, parity) of the last barrier wait that timed out, zeros if none.
+        Lives in mapped host memory, so it is readable after a trap has poisoned the CUDA context."""
+        buf = (C.c_uint32 * 4)()
+        check(self._lib.nwx_ctx_last_diag(self._ctx, buf), "nwx_ctx_last_diag")
+        return tuple(int(v) for v in buf)
+
     STAGES = ("coarse_z", "dirbias_coarse", "mlp_coarse", "composite_coarse", "sample_pdf", "dirbias_fine",
               "mlp_fine", "composite_fine")
 
@@ -220,6 +227,27 @@ class Engine:
                                                  _stream()), "nwx_mlp_forward_embedded")
         return raw
 
+    # ---- training batch sampling ------------------------------------------------------------
+    def sample_training_batch(self, rays_bank: torch.Tensor, rgb_bank: torch.Tensor, n: int, seed: int, offset: int,
+                              want_indices: bool = False):
+        """_sample_training_data (training handler:341-370) without leaving the device: one random image of
+        rays_bank [num_img, num_ray, 11], n random pixels of it with replacement, and the gather of the rays and
+        of the ground-truth pixels rgb_bank [num_img, num_ray, 3] -> (rays [n,11], gt [n,3][, idx int64 [1+n]])."""
+        if not (rays_bank.is_cuda and rgb_bank.is_cuda and rays_bank.is_contiguous() and rgb_bank.is_contiguous()
+                and rays_bank.dtype == torch.float32 and rgb_bank.dtype == torch.float32):
+            raise _lib.NwxError("sample_training_batch: banks must be contiguous fp32 CUDA tensors")
+        num_img, num_ray, ray_dim = rays_bank.shape
+        if tuple(rgb_bank.shape) != (num_img, num_ray, 3):
+            raise _lib.NwxError(f"rgb bank must be {(num_img, num_ray, 3)}, got {tuple(rgb_bank.shape)}")
+        dev = rays_bank.device
+        rays = torch.empty((n, ray_dim), device=dev)
+        gt = torch.empty((n, 3), device=dev)
+        idx = torch.empty((1 + n,), device=dev, dtype=torch.int64) if want_indices else None
+        check(self._lib.nwx_sample_training_batch(rays_bank.data_ptr(), rgb_bank.data_ptr(), num_img, num_ray, ray_dim, n,
+                                                  seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, rays.data_ptr(),
+                                                  gt.data_ptr(), _ptr(idx), _stream()), "nwx_sample_training_batch")
+        return (rays, gt, idx) if want_indices else (rays, gt)
+
     # ---- whole chunk ---------------------------------------------------------------------
     def render_rays(self, rays: torch.Tensor, n_samples: int = 64, n_importance: int = 128,
                     white_bkgd: bool = False, want: Iterable[str] = REFERENCE_KEYS,
@@ -233,8 +261,10 @@ class Engine:
         in-kernel counter-based draws for whichever of t_rand / u / noise_* is not given."""
         rays = _f32(rays, "rays")
         N, dev = rays.shape[0], rays.device
-        want = set(want) | {"rgb_fine"}
+        want = set(want)
         res = dict(out) if out else {}
+        if not ({"rgb_fine", "rgb8_fine"} & (want | set(res))):
+            want.add("rgb_fine")                  # the library needs one of the two final images
         unknown = [k for k in set(want) | set(res) if k not in _OUT_SHAPES]
         if unknown:
             raise _lib.NwxError(f"render_rays: unknown output(s) {sorted(unknown)}; known: {sorted(_OUT_SHAPES)}")

@@ -60,6 +60,7 @@ class NeRFReplicaInferenceHandler:
         self._nerf_net_fine: Optional[NeRFModel] = None
         self._embed_fcn = self._embed_dirs_fcn = None
         self.max_rays_per_launch = 1 << 20       # scratch is ~6.4 KB per ray
+        self._host_frames: Optional[torch.Tensor] = None     # persistent pinned read-back buffer (uint8)
 
     @property
     def _device(self) -> torch.device:
@@ -98,6 +99,8 @@ class NeRFReplicaInferenceHandler:
         self._engine = _engine.Engine(self._device)
         self._engine.load_weights(_engine.COARSE, self._nerf_net_coarse.state_dict())
         self._engine.load_weights(_engine.FINE, self._nerf_net_fine.state_dict())
+        # size the scratch for one frame now, so that no render call allocates (or frees) device memory
+        self._engine.reserve(max(1, min(self.max_rays_per_launch, self._n_pix)), self._n_samples, self._n_importance)
 
     @staticmethod
     def transform_state_dict(state_dict: Dict[str, Any]) -> Dict[str, Any]:
@@ -124,21 +127,41 @@ class NeRFReplicaInferenceHandler:
         """Many views of one spot in one launch sequence (the GUI's camera sweep) -> uint8 [B,H,W,3]."""
         return self.render_poses(get_camera_poses_from_list_of_coordinates(init_coordinates, list(coordinates)))
 
+    def _pinned_frames(self, nbytes: int) -> torch.Tensor:
+        """Persistent page-locked host buffer for the uint8 read-back (grown on demand, never per frame)."""
+        if self._host_frames is None or self._host_frames.numel() < nbytes:
+            self._host_frames = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+        return self._host_frames[:nbytes]
+
+    def render_rays_u8(self, c2w_dev: torch.Tensor, ray0: int, count: int, out: Optional[torch.Tensor] = None
+                       ) -> torch.Tensor:
+        """uint8 pixels [count,3] of the rays [ray0, ray0+count) of the B*H*W rays of `c2w_dev` ([B,4,4] on the
+        device): raygen + the 8-launch render, the compositing kernel writes the bytes.  This is the unit the
+        multi-GPU path shards (nwx/dist.py)."""
+        eng = self.engine
+        rgb8 = torch.empty((count, 3), device=self._device, dtype=torch.uint8) if out is None else out
+        for s in range(0, count, self.max_rays_per_launch):
+            n = min(self.max_rays_per_launch, count - s)
+            rays = eng.raygen(c2w_dev, self._img_h, self._img_w, self._fx, self._fy, self._cx, self._cy,
+                              self._depth_close_bound, self._depth_far_bound, True, ray0=ray0 + s, nrays=n)
+            eng.render_rays(rays, self._n_samples, self._n_importance, self._white_bkgd, want=("rgb8_fine",),
+                            out={"rgb8_fine": rgb8[s:s + n]})
+        return rgb8
+
+    def frames_to_host(self, rgb8: torch.Tensor, B: int) -> np.ndarray:
+        """Device uint8 [B*H*W,3] -> a fresh host array [B,H,W,3]: one cudaMemcpyAsync into the persistent
+        pinned buffer on the current stream, one stream synchronisation, one host memcpy."""
+        host = self._pinned_frames(rgb8.numel())
+        host.copy_(rgb8.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self._device).synchronize()
+        return host.numpy().reshape(B, self._img_h, self._img_w, 3).copy()
+
     @torch.no_grad()
     def render_poses(self, c2w: torch.Tensor) -> np.ndarray:
         """[B,4,4] camera-to-world poses -> uint8 [B,H,W,3]; H2D 64 B per view, D2H 3 B per pixel."""
-        eng = self.engine
         B = c2w.shape[0]
-        total = B * self._n_pix
         c2w_dev = c2w.to(self._device, dtype=torch.float32, non_blocking=True)
-        rgb8 = torch.empty((total, 3), device=self._device, dtype=torch.uint8)
-        for start in range(0, total, self.max_rays_per_launch):
-            n = min(self.max_rays_per_launch, total - start)
-            rays = eng.raygen(c2w_dev, self._img_h, self._img_w, self._fx, self._fy, self._cx, self._cy,
-                              self._depth_close_bound, self._depth_far_bound, True, ray0=start, nrays=n)
-            eng.render_rays(rays, self._n_samples, self._n_importance, self._white_bkgd, want=("rgb8_fine",),
-                            out={"rgb8_fine": rgb8[start:start + n]})
-        return rgb8.cpu().numpy().reshape(B, self._img_h, self._img_w, 3)
+        return self.frames_to_host(self.render_rays_u8(c2w_dev, 0, B * self._n_pix), B)
 
     def _render_rays(self, flat_rays: torch.Tensor) -> Dict[str, torch.Tensor]:
         """handler:187-201 -> the 11-key dict for [n,11] rays.  The reference chunks by

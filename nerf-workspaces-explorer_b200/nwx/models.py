@@ -1,8 +1,12 @@
 """Reference entry points of nerf/models/{embedding,nerf_model,model_utils}.py on the CUDA engine.
 
 Same class / function names, constructor arguments, state_dict keys and return values as the
-reference, so its callers (handlers, nerf/train.py) keep working; the arithmetic runs in the
-hand-written kernels of libnwx (fused PE + tcgen05 MLP, warp-scan compositing).
+reference, so its inference callers (the handlers' _volumetric_rendering, application/workspace.py)
+keep working; the arithmetic runs in the hand-written kernels of libnwx (fused PE + tcgen05 MLP,
+warp-scan compositing).  These entry points are FORWARD ONLY: the reference's training loop
+(total_loss.backward() through run_network / raw2outputs, training handler:305-308) is served by
+nwx.Trainer / nwx.NeRFReplicaTrainingHandler, whose fused kernels produce the gradients; calling
+.backward() through NeRFModel.forward raises instead of silently leaving the weights untouched.
 """
 from __future__ import annotations
 
@@ -45,6 +49,33 @@ class Embedding:
 
     def embed(self, inputs: torch.Tensor) -> torch.Tensor:
         return _engine.embed(inputs, self._num_freqs, self._scalar_factor)
+
+
+class _ForwardOnly(torch.autograd.Function):
+    """Marks the fused forward's output as depending on the parameters, so that a backward() through it fails
+    loudly (the kernel keeps no autograd graph) instead of silently producing no gradients."""
+
+    @staticmethod
+    def forward(ctx, out, *params):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NwxError("NeRFModel.forward / run_network / raw2outputs run forward-only CUDA kernels: gradients exist "
+                       "only through nwx.Trainer or nwx.NeRFReplicaTrainingHandler.step (fused forward + backward + "
+                       "Adam). Wrap inference calls in torch.no_grad().")
+
+
+class _Probe:
+    """run_network's way of recognising a thin wrapper around a NeRFModel (the handlers pass
+    `lambda x: self._nerf_net_fine(x, self._endpoint_feat)`, inference handler:248): the callable is invoked
+    once on an EMPTY [0,90] input while this probe is armed; NeRFModel.forward records itself and returns a
+    sentinel, and only a callable that hands its input to exactly one supported NeRFModel and returns that
+    model's output unchanged is taken onto the fused path."""
+    active: Optional["_Probe"] = None
+
+    def __init__(self):
+        self.model, self.calls, self.x, self.out, self.show_endpoint = None, 0, None, None, False
 
 
 class NeRFModel(nn.Module):
@@ -98,16 +129,30 @@ class NeRFModel(nn.Module):
 
     def forward(self, x: torch.Tensor, show_endpoint: bool = False) -> torch.Tensor:
         """x [P,90] = (embedded xyz 63, embedded view dir 27) -> [P,4] raw (rgb, sigma)."""
+        probe = _Probe.active
+        if probe is not None:                         # run_network is asking "who are you?" (see _Probe)
+            probe.calls += 1
+            probe.model, probe.x, probe.show_endpoint = self, x, bool(show_endpoint)
+            probe.out = x.new_empty(tuple(x.shape[:-1]) + (4,))
+            return probe.out
         if show_endpoint:
             raise NwxError("show_endpoint=True (endpoint_feat) is not implemented; every shipped config "
                            "sets endpoint_feat: False")
         lead = x.shape[:-1]
         out = self._packed_engine().mlp_forward_embedded(_engine.COARSE, x.reshape(-1, x.shape[-1]))
-        return out.reshape(*lead, 4)
+        return self._forward_only(out.reshape(*lead, 4), x)
+
+    def _forward_only(self, out: torch.Tensor, *inputs: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled():
+            live = [t for t in list(self.parameters()) + list(inputs) if t.requires_grad]
+            if live:
+                return _ForwardOnly.apply(out, *live)
+        return out
 
     def forward_points(self, pts: torch.Tensor, viewdirs: torch.Tensor, pts_per_dir: int = 1) -> torch.Tensor:
         """Fused path: raw points [P,3] and unit view directions (one per `pts_per_dir` points)."""
-        return self._packed_engine().mlp_forward_points(_engine.COARSE, pts, viewdirs, pts_per_dir)
+        out = self._packed_engine().mlp_forward_points(_engine.COARSE, pts, viewdirs, pts_per_dir)
+        return self._forward_only(out, pts, viewdirs)
 
 
 def _is_standard_embed(fn, num_freqs: int, scale: float) -> bool:
@@ -115,18 +160,38 @@ def _is_standard_embed(fn, num_freqs: int, scale: float) -> bool:
     return isinstance(owner, Embedding) and owner.num_freqs == num_freqs and owner.scalar_factor == scale
 
 
+def _resolve_model(fn: Callable, like: torch.Tensor) -> Optional[NeRFModel]:
+    """The NeRFModel behind `fn` if `fn` is one, or a pass-through wrapper around one (see _Probe); else None."""
+    if isinstance(fn, NeRFModel):
+        return fn if fn._supported() else None
+    probe, x = _Probe(), like.new_empty((0, 90))
+    prev, _Probe.active = _Probe.active, probe
+    try:
+        out = fn(x)
+    except Exception:  # noqa: BLE001  (an arbitrary callable that cannot take the probe: literal path)
+        return None
+    finally:
+        _Probe.active = prev
+    if probe.calls == 1 and probe.x is x and out is probe.out and not probe.show_endpoint and probe.model._supported():
+        return probe.model
+    return None
+
+
 def run_network(inputs: torch.Tensor, viewdirs: Optional[torch.Tensor], fn: Callable, embed_fn: Callable,
                 embeddirs_fn: Optional[Callable], netchunk: Optional[int] = 1024 * 64) -> torch.Tensor:
     """model_utils.py:13-30: [N,S,3] points (+ [N,3] view dirs) -> [N,S,4].
 
-    When `fn` is a NeRFModel and the embedders are the standard Embedding(10,10)/(4,1) pair the
-    whole call is ONE fused kernel (no embedding materialised, no chunk loop).  Any other callable
-    (e.g. the handlers' lambda around the fine model) takes the literal path: embed kernels,
+    When `fn` is a NeRFModel -- or a thin wrapper that passes its input to one and returns the result, such
+    as the handlers' `lambda x: self._nerf_net_fine(x, self._endpoint_feat)` (inference handler:248) -- and
+    the embedders are the standard Embedding(10,10)/(4,1) pair, the whole call is ONE fused kernel (no
+    embedding materialised, no chunk loop).  Any other callable takes the literal path: embed kernels,
     concatenation, and `fn` per chunk."""
-    if (isinstance(fn, NeRFModel) and viewdirs is not None and _is_standard_embed(embed_fn, 10, 10)
-            and _is_standard_embed(embeddirs_fn, 4, 1) and inputs.dim() == 3):
-        n, s, _ = inputs.shape
-        return fn.forward_points(inputs.reshape(-1, 3), viewdirs, pts_per_dir=s).reshape(n, s, 4)
+    if (viewdirs is not None and inputs.dim() == 3 and inputs.is_cuda and _is_standard_embed(embed_fn, 10, 10)
+            and _is_standard_embed(embeddirs_fn, 4, 1)):
+        model = _resolve_model(fn, inputs)
+        if model is not None:
+            n, s, _ = inputs.shape
+            return model.forward_points(inputs.reshape(-1, 3), viewdirs, pts_per_dir=s).reshape(n, s, 4)
     flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
     embedded = embed_fn(flat)
     if viewdirs is not None:

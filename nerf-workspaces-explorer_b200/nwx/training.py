@@ -27,6 +27,22 @@ def param_offsets() -> Tuple[int, ...]:
     return tuple(int(v) for v in buf)
 
 
+def rank_of(group: Optional[dist.ProcessGroup] = None) -> int:
+    """This process' rank in the data-parallel group (0 without torch.distributed)."""
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def world_of(group: Optional[dist.ProcessGroup] = None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank_seed(seed: int, group: Optional[dist.ProcessGroup] = None) -> int:
+    """Seed of the per-rank random streams (pixel sampling, jitter, importance uniforms, sigma noise): every
+    rank must draw a DIFFERENT batch, otherwise the all-reduce averages N copies of one gradient and data
+    parallelism buys nothing.  Parameter initialisation keeps the unshifted seed (identical on every rank)."""
+    return int(seed) + rank_of(group)
+
+
 def allreduce_sum_(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> float:
     """Sum `flat` over the ranks in place (one collective for both networks' gradients) and return
     the factor that turns the sum into the data-parallel mean (1 / world_size): per-rank batches
@@ -47,7 +63,7 @@ class Trainer:
                  lr: float = 5e-4, lr_decay_rate: float = 0.1, lr_decay_steps: int = 50000,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, n_samples: int = 64,
                  n_importance: int = 128, white_bkgd: bool = False, perturb: float = 1.0, raw_noise_std: float = 1.0,
-                 group: Optional[dist.ProcessGroup] = None, seed: int = 0):
+                 group: Optional[dist.ProcessGroup] = None, seed: int = 0, overlap_allreduce: bool = True):
         self.engine, self.device, self.group = eng, eng.device, group
         self.lr0, self.lr, self.lr_decay_rate, self.lr_decay_steps = lr, lr, lr_decay_rate, lr_decay_steps
         self.betas, self.eps = betas, eps
@@ -63,7 +79,18 @@ class Trainer:
         self.v = torch.zeros_like(self.params)
         self.loss = torch.zeros(2, device=self.device, dtype=torch.float64)
         self.opt_steps = 0
-        self.seed, self.draws = seed, 0          # in-kernel RNG key and per-call offset
+        # in-kernel RNG key (rank-folded: each rank draws its own jitter / u / noise / pixels) and per-call offset
+        self.base_seed, self.seed, self.draws = int(seed), rank_seed(seed, group), 0
+        self.world = world_of(group)
+        if self.world > 1:
+            # identical parameters on every rank regardless of what each rank was constructed with
+            dist.broadcast(self.params, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        # data-parallel overlap: the coarse network's gradients are complete before the fine network's
+        # backward starts, so their all-reduce runs on a side stream underneath it
+        self._overlap = bool(overlap_allreduce) and self.world > 1 and self.device.type == "cuda"
+        self._comm_stream = torch.cuda.Stream(self.device) if self._overlap else None
+        self._ev_coarse = torch.cuda.Event() if self._overlap else None
+        self._coarse_reduced = False
         self.pack()
 
     # ---- parameters ------------------------------------------------------------------------
@@ -106,8 +133,11 @@ class Trainer:
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "params": list(range(idx))}
+        # nwx_rng: not a reference key (its loaders ignore it); lets a resumed run continue the random streams
+        # instead of replaying the draws of steps 0..k
         return {"global_step": global_step, "network_coarse_state_dict": sds[0], "network_fine_state_dict": sds[1],
-                "optimizer_state_dict": {"state": state, "param_groups": [group]}}
+                "optimizer_state_dict": {"state": state, "param_groups": [group]},
+                "nwx_rng": {"seed": self.base_seed, "draws": self.draws}}
 
     def save_checkpoint(self, path: str, global_step: int) -> None:
         torch.save(self.checkpoint(global_step), path)
@@ -129,8 +159,13 @@ class Trainer:
                     self.opt_steps = int(st["step"])
                     idx += 1
             self.lr = float(opt["param_groups"][0]["lr"])
+        step = int(ckpt.get("global_step", 0))
+        rng = ckpt.get("nwx_rng")
+        # continue the random streams: our own checkpoints carry the draw counter; a reference checkpoint does
+        # not, there the optimiser step count (one render per step) is the best available offset
+        self.draws = int(rng["draws"]) if rng else max(self.draws, self.opt_steps)
         self.pack()
-        return int(ckpt.get("global_step", 0))
+        return step
 
     # ---- one step ----------------------------------------------------------------------------
     def forward_backward(self, rays: torch.Tensor, gt_rgb: torch.Tensor, t_rand: Optional[torch.Tensor] = None,
@@ -152,17 +187,34 @@ class Trainer:
                           *rng.fields())
         rgb_c = torch.empty((N, 3), device=dev) if want_rgb else None
         rgb_f = torch.empty((N, 3), device=dev) if want_rgb else None
+        if self._overlap:      # the previous step's side-stream all-reduce must be done with grads[COARSE]
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        ev = None
+        if self._overlap:
+            self._ev_coarse.record()       # torch creates the handle lazily; the library re-records it mid-call
+            ev = self._ev_coarse.cuda_event
         io = TrainIO(rays.data_ptr(), gt.data_ptr(), self.grads[COARSE].data_ptr(), self.grads[FINE].data_ptr(),
-                     self.loss.data_ptr(), _ptr(rgb_c), _ptr(rgb_f))
+                     self.loss.data_ptr(), _ptr(rgb_c), _ptr(rgb_f), ev)
         check(self.engine._lib.nwx_train_fwd_bwd(self.engine._ctx, C.byref(io), N, C.byref(opts), _stream()),
               "nwx_train_fwd_bwd")
+        self._coarse_reduced = False
+        if self._overlap:
+            self._comm_stream.wait_event(self._ev_coarse)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(self.grads[COARSE], group=self.group)      # underneath the fine network's backward
+            self._coarse_reduced = True
         return (self.loss, rgb_c, rgb_f) if want_rgb else self.loss
 
     def optimizer_step(self, global_step: int) -> None:
         """All-reduce (mean) the gradients across ranks, Adam, re-pack, then the reference's
         learning-rate schedule lr = lr0 * rate^(step/decay_steps) (training handler:312-315),
         which -- as in the reference -- takes effect from the NEXT step."""
-        scale = allreduce_sum_(self.grads, self.group)               # 4.77 MB, one NCCL call
+        if self._coarse_reduced:                                      # coarse half already in flight on the side stream
+            scale = allreduce_sum_(self.grads[FINE], self.group)     # 2.38 MB
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+            self._coarse_reduced = False
+        else:
+            scale = allreduce_sum_(self.grads, self.group)           # 4.77 MB, one NCCL call
         self.opt_steps += 1
         n = self.params.numel()
         check(self.engine._lib.nwx_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
@@ -172,9 +224,10 @@ class Trainer:
         self.lr = self.lr0 * (self.lr_decay_rate ** (global_step / self.lr_decay_steps))
 
     def step(self, rays: torch.Tensor, gt_rgb: torch.Tensor, global_step: int, **rand) -> torch.Tensor:
-        loss = self.forward_backward(rays, gt_rgb, **rand)
+        """One optimisation step; returns a COPY of the two MSE terms (self.loss is overwritten every step)."""
+        self.forward_backward(rays, gt_rgb, **rand)
         self.optimizer_step(global_step)
-        return loss
+        return self.loss.clone()
 
 
 class NeRFReplicaTrainingHandler:
@@ -184,7 +237,7 @@ class NeRFReplicaTrainingHandler:
 
     def __init__(self, office_name: str, config: Optional[Mapping], rays_train: torch.Tensor, train_rgbs: torch.Tensor,
                  sd_coarse: Optional[Mapping] = None, sd_fine: Optional[Mapping] = None,
-                 device: Optional[torch.device] = None, seed: int = 0):
+                 device: Optional[torch.device] = None, seed: int = 0, group: Optional[dist.ProcessGroup] = None):
         from .synthetic import random_state_dicts
         cfg = default_config() if config is None else config
         self._office_name, self._config = office_name, cfg
@@ -192,8 +245,8 @@ class NeRFReplicaTrainingHandler:
         self._n_rays = number(rnd["n_rays"])
         self._img_h, self._img_w = int(cfg["experiment"]["image_height"]), int(cfg["experiment"]["image_width"])
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.rays_train = rays_train.to(dev).float()               # [num_images, H*W, 11]
-        self._train_rgbs = train_rgbs.to(dev).float().reshape(rays_train.shape[0], -1, 3)
+        self.rays_train = rays_train.to(dev).float().contiguous()   # [num_images, H*W, 11]
+        self._train_rgbs = train_rgbs.to(dev).float().reshape(rays_train.shape[0], -1, 3).contiguous()
         if sd_coarse is None:
             sd_coarse, sd_fine = random_state_dicts(seed, alpha_bias=None)
         self._engine = _engine.Engine(dev)
@@ -202,17 +255,17 @@ class NeRFReplicaTrainingHandler:
                                lr_decay_steps=int(trn["learning_rate_decay_steps"]),
                                n_samples=int(rnd["n_samples"]), n_importance=int(rnd["n_importance"]),
                                white_bkgd=bool(rnd["white_background"]), perturb=float(rnd["perturb"]),
-                               raw_noise_std=float(rnd["raw_noise_std"]), seed=seed)
-        self._gen = torch.Generator(device=dev).manual_seed(seed)
+                               raw_noise_std=float(rnd["raw_noise_std"]), seed=seed, group=group)
         self._chunk = number(cfg.get("model", {}).get("chunk", 1024 * 32))   # rays per render call (yaml model.chunk)
         self._train_mode, self._weights_version = True, -1
 
-    def _sample_training_data(self):
-        """One random image, n_rays random pixels with replacement (training handler:341-370)."""
-        num_img, num_ray, _ = self.rays_train.shape
-        img = int(torch.randint(0, num_img, (1,), device=self.rays_train.device, generator=self._gen))
-        pix = torch.randint(0, num_ray, (self._n_rays,), device=self.rays_train.device, generator=self._gen)
-        return self.rays_train[img, pix], self._train_rgbs[img, pix]
+    def _sample_training_data(self, want_indices: bool = False):
+        """One random image, n_rays random pixels with replacement (training handler:341-370) -- drawn and
+        gathered by ONE kernel on the device (no host round trip, no synchronisation); the draws are keyed by
+        the trainer's rank-folded seed and its draw counter, so every rank and every step gets its own batch."""
+        tr = self.trainer
+        return self._engine.sample_training_batch(self.rays_train, self._train_rgbs, self._n_rays, tr.seed, tr.draws,
+                                                  want_indices=want_indices)
 
     # ---- forward-only renders (eval renders of the reference's loop, training handler:479-532) ----
     def set_train_mode(self, on: bool) -> None:
@@ -256,8 +309,7 @@ class NeRFReplicaTrainingHandler:
 
     def step(self, global_step: int) -> Dict[str, torch.Tensor]:
         rays, gt = self._sample_training_data()
-        loss = self.trainer.step(rays, gt, global_step)
-        mse = loss.clone()
+        mse = self.trainer.step(rays, gt, global_step)
         psnr = -10.0 * torch.log10(mse)                            # mse2psnr, model_utils.py:8
         return {"rgb_loss_coarse": mse[0], "rgb_loss_fine": mse[1], "total_loss": mse.sum(),
                 "psnr_coarse": psnr[0], "psnr_fine": psnr[1]}

@@ -73,6 +73,25 @@ def test_gradient_allreduce_mean_gloo_world2():
     assert allreduce_sum_(t) == 1.0 and torch.equal(t, torch.ones(4))      # no process group: identity
 
 
+def _seed_worker(rank: int, world: int, port: int, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nwx.training import rank_of, rank_seed, world_of
+    results[rank] = (rank_seed(7), rank_of(), world_of())
+    dist.destroy_process_group()
+
+
+def test_per_rank_random_streams_gloo_world2():
+    """every rank must draw its own batch / jitter / noise -- the RNG key folds the rank in."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_seed_worker, args=(world, port, results), nprocs=world, join=True)
+        assert dict(results) == {0: (7, 0, 2), 1: (8, 1, 2)}
+    from nwx.training import rank_seed
+    assert rank_seed(7) == 7                                       # no process group: unshifted
+
+
 def test_single_process_is_identity():
     from nwx.dist import render_sharded
     assert torch.equal(render_sharded(1000, _fake_render), _fake_render(0, 1000))
