@@ -8,16 +8,26 @@ samples (BASELINE.json metric / configs[1], [2]).
 
 One step = one batch of N_gpus 640x480 views (307 200 rays each, Replica-shaped synthetic poses,
 random-init weights of the reference architecture).  The batch's rays are sharded contiguously
-across ranks (one frame's worth per GPU: weak scaling), each rank renders its shard with the
-7-launch libnwx sequence, and the uint8 pixel tiles are exchanged with one NCCL all-gather.
+across ranks (one frame's worth per GPU: weak scaling), each rank generates and renders its shard
+with the 9-launch libnwx sequence (raygen + 8), and the uint8 pixel tiles are exchanged with one
+NCCL all-gather.
 
-  value : device-resident throughput -- rays already in HBM, result left in HBM.
-  e2e   : the same through the public handler API (NeRFReplicaInferenceHandler.render_poses):
-          poses come from pinned host memory, the uint8 frame is read back to the host.
+  value : device-resident throughput -- poses already in HBM, gathered uint8 frames left in HBM.
+  e2e   : the same through the public API with HOST buffers: N = 1 NeRFReplicaInferenceHandler.render_poses,
+          N > 1 nwx.dist.render_poses_sharded(..., to_host=True) -- poses come from pinned host memory, the
+          gathered uint8 frames are read back to the host on every rank.
   roofline : the fused PE+MLP tcgen05 kernel (both launches of a step), CUDA events recorded
           around it on the launch stream inside the timed region, against the measured bf16 peak.
-  cpu_baseline : the CPU oracle (port of the reference path) on this box's host cores, on a
-          bounded 16384-ray sample of the same frame.
+  strong : BASELINE configs[2] as north_star words it -- ONE 640x480 frame partitioned across the N ranks
+          (row tiles), all-gather of the uint8 tiles included; the per-rank fixed cost that limits it is listed.
+  train  : BASELINE configs[3] -- NeRFReplicaTrainingHandler.step, 4096 rays per GPU, gradient all-reduce.
+  function_level (N = 1) : the reference handler's own call sequence on nwx's entry points (run_network with
+          the handler's lambda, raw2outputs, sample_pdf, torch.sort), in the reference's 8192-ray chunks.
+  gpu_eager_baseline (N = 1) : what the reference executes on this GPU -- the oracle port with CUDA tensors
+          (torch eager, fp32, TF32 off, chunk 8192 / net_chunk 32768), one full frame.
+  cpu_baseline (N = 1) : the CPU oracle (port of the reference path) on this box's host cores, on a
+          bounded 16384-ray sample of the same frame; once more with autograd anomaly detection on, as the
+          reference ships it (nerf_model.py:7).
 --impl reference times that CPU path alone, as the reference arm.
 """
 import argparse
@@ -45,6 +55,12 @@ POINTS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)
 WORKLOAD = ("640x480 Replica-shaped frame, 64 coarse + 128 fine samples, one view per GPU, "
             "rays sharded contiguously across ranks, uint8 pixel tiles all-gathered (NCCL)")
 CPU_SAMPLE_RAYS = 16384                  # two reference inference chunks (yaml inference.chunk = 8192)
+# training step (BASELINE configs[3]): fwd + bwd FLOP per point and the HBM bytes per point the
+# step moves by construction ("HBM traffic per point and step")
+TRAIN_RAYS_PER_GPU = 4096
+FLOP_PER_POINT_TRAIN = 3489024
+TRAIN_BYTES_PER_POINT = 19.6e3
+TRAIN_BANK = (180, 240, 320)             # images, H, W of the synthetic ray / pixel banks
 
 
 def synthetic_setup():
@@ -117,12 +133,16 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------- CPU reference ----
-def cpu_reference_rays_per_s(n_rays: int, repeats: int = 1, warm: int = 256):
+def cpu_reference_rays_per_s(n_rays: int, repeats: int = 1, warm: int = 256, anomaly: bool = False):
     """The oracle's port of the reference CPU path (create_rays -> _volumetric_rendering with the
-    reference's chunking) on a strided n_rays sample of the 640x480 frame, all host threads."""
+    reference's chunking) on a strided n_rays sample of the 640x480 frame, all host threads.
+    anomaly=True: with torch.autograd.set_detect_anomaly(True), which importing the reference's
+    nerf_model.py / embedding.py switches on globally (nerf_model.py:7)."""
     from oracle import nerf_oracle as orc        # the CPU baseline is the one place bench.py runs oracle/
     sd_c, sd_f, poses, (fx, fy, cx, cy) = synthetic_setup()
     torch.set_num_threads(os.cpu_count() or 1)
+    prev_anomaly = torch.is_anomaly_enabled()
+    torch.autograd.set_detect_anomaly(anomaly)
     rays = orc.create_rays(1, poses[:1], H, W, fx, fy, cx, cy, NEAR, FAR, True)[0]
     idx = torch.linspace(0, rays.shape[0] - 1, n_rays).long()
     sample = rays[idx].contiguous()
@@ -134,7 +154,31 @@ def cpu_reference_rays_per_s(n_rays: int, repeats: int = 1, warm: int = 256):
             t0 = time.perf_counter()
             orc.render_rays(sample, sd_c, sd_f, cfg, keys=("rgb_fine",))
             best = min(best, time.perf_counter() - t0)
+    torch.autograd.set_detect_anomaly(prev_anomaly)
     return n_rays / best, best, torch.get_num_threads()
+
+
+def gpu_eager_frame_ms(dev):
+    """What the reference executes on a GPU: torch eager, fp32 (TF32 off), rays built on the CPU and moved
+    with .cuda() (inference handler:172-174), 8192-ray chunks x 32768-point network chunks -- the oracle port
+    with CUDA tensors, one full 640x480 frame.  A baseline leg, like cpu_baseline."""
+    from oracle import nerf_oracle as orc
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd_c, sd_f, poses, (fx, fy, cx, cy) = synthetic_setup()
+    sd_c = {k: v.to(dev) for k, v in sd_c.items()}
+    sd_f = {k: v.to(dev) for k, v in sd_f.items()}
+    cfg = orc.RenderConfig()
+    with torch.no_grad():
+        warm = orc.create_rays(1, poses[:1], H, W, fx, fy, cx, cy, NEAR, FAR, True)[0][:2 * cfg.chunk].to(dev)
+        orc.render_rays(warm, sd_c, sd_f, cfg, keys=("rgb_fine",))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        rays = orc.create_rays(1, poses[:1], H, W, fx, fy, cx, cy, NEAR, FAR, True).to(dev)     # CPU raygen + H2D
+        out = orc.render_rays(rays[0], sd_c, sd_f, cfg, keys=("rgb_fine",))
+        img = orc.to8b(out["rgb_fine"].cpu().numpy().reshape(H, W, 3))                         # D2H + to8b_np
+        ms = (time.perf_counter() - t0) * 1e3
+    return ms, img
 
 
 def run_reference_arm(args):
@@ -163,11 +207,14 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------- GPU arm ----
+NCU_MLP_CAPTURE = os.path.join("profiles", "r01_ncu_mlp_full_fold.csv")
+
+
 def mlp_dram_traffic_per_step():
     """dram__bytes_read.sum + dram__bytes_write.sum of the two mlp_fused_kernel launches of one step,
-    from the committed `ncu --set full` capture (profiles/r01_ncu_mlp_full.csv); None if absent."""
+    from the committed `ncu --set full` capture (NCU_MLP_CAPTURE) -- a static figure, stated as such; None if absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_ncu_mlp_full_fold.csv")
+    path = os.path.join(ROOT, NCU_MLP_CAPTURE)
     if not os.path.exists(path):
         return None
     with open(path) as f:
@@ -184,6 +231,14 @@ def mlp_dram_traffic_per_step():
     return total * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) / (N_SAMPLES + N_IMPORTANCE)
 
 
+def measured_hbm_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f).get("hbm_gbs", 6538.9))
+    return 6538.9
+
+
 def measured_peak_tflops():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -197,7 +252,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
     import nwx
     from nwx import engine as E
-    from nwx.dist import gather_tiles, shard_range
+    from nwx.dist import gather_tiles, render_poses_sharded, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,9 +277,10 @@ def run_gpu_arm(args):
     ray0, n_local = shard_range(total_rays, rank, world)   # contiguous ray range of this rank (nwx/dist.py)
     eng.reserve(n_local, N_SAMPLES, N_IMPORTANCE)
     eng.set_profiling(True)
-    rays = eng.raygen(batch_poses, H, W, fx, fy, cx, cy, NEAR, FAR, True, ray0=ray0, nrays=n_local)
+    poses_dev = batch_poses.to(dev)
     rgb8 = torch.empty((n_local, 3), device=dev, dtype=torch.uint8)
-    pinned_pose = batch_poses[rank:rank + 1].clone().pin_memory()
+    pinned_batch = batch_poses.clone().pin_memory()
+    pinned_one = batch_poses[:1].clone().pin_memory()
 
     def barrier():
         if world > 1:
@@ -232,12 +288,17 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     def device_step():
-        eng.render_rays(rays, N_SAMPLES, N_IMPORTANCE, False, want=("rgb8_fine",), out={"rgb8_fine": rgb8})
+        handler.render_rays_u8(poses_dev, ray0, n_local, out=rgb8)   # raygen + the 8-launch render of this rank's shard
         return gather_tiles(rgb8, total_rays)          # NCCL all-gather of the uint8 pixel tiles (identity at N=1)
 
     def e2e_step():
-        img = handler.render_poses(pinned_pose)       # H2D pose, render, D2H uint8 frame (public API)
-        return img
+        # public API, host buffers: pinned poses -> device, render (sharded + all-gather at N > 1), frames -> host
+        if world == 1:
+            return handler.render_poses(pinned_batch)
+        return render_poses_sharded(handler, pinned_batch, to_host=True)
+
+    def strong_step():
+        return render_poses_sharded(handler, pinned_one, to_host=True)   # ONE frame over all ranks, to the host
 
     def timed(fn, steps, collect_stages=False):
         barrier()
@@ -255,6 +316,13 @@ def run_gpu_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # max over ranks
         return float(ms.item()), stages
 
+    def max_over_ranks(d):
+        keys = sorted(d)
+        t = torch.tensor([d[k] for k in keys], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(zip(keys, [float(v) for v in t]))
+
     for _ in range(args.warmup):
         device_step()
     sampler = ClockSampler(local)
@@ -269,6 +337,27 @@ def run_gpu_arm(args):
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms, _ = timed(e2e_step, e2e_steps)
 
+    # ---- strong scaling: one frame over N ranks (BASELINE configs[2]) ----
+    for _ in range(3):
+        strong_step()
+    strong_steps = max(5, min(args.steps, 20))
+    strong_ms, strong_stages = timed(strong_step, strong_steps, collect_stages=True)
+    smean = lambda k: sum(s[k] for s in strong_stages) / len(strong_stages)
+    strong_stage_ms = max_over_ranks({k: smean(k) for k in E.Engine.STAGES})
+    strong = {
+        "workload": "ONE 640x480 frame (64+128 samples) partitioned into N contiguous row tiles, NCCL all-gather of the "
+                    "uint8 tiles, frame read back to the host on every rank (nwx.dist.render_poses_sharded)",
+        "n_gpus": world, "ms_per_frame": strong_ms / strong_steps, "rays_per_s": H * W * strong_steps / (strong_ms * 1e-3),
+        "steps": strong_steps, "rays_per_rank": shard_range(H * W, 0, world)[1],
+        "stages_ms_max_over_ranks": strong_stage_ms,
+        "mlp_ms": strong_stage_ms["mlp_coarse"] + strong_stage_ms["mlp_fine"],
+        "non_mlp_ms": strong_ms / strong_steps - strong_stage_ms["mlp_coarse"] - strong_stage_ms["mlp_fine"],
+        "limiter": "non_mlp_ms = the per-rank cost that does not shrink like 1/N at this size: 9 launches, sample_pdf / "
+                   "compositing / dirbias at small grids, the all-gather and the host read-back",
+    }
+
+    train = run_train_bench(nwx, dev, world, rank, barrier, args)
+
     rays_per_step = world * n_local
     value = rays_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = rays_per_step * e2e_steps / (e2e_ms * 1e-3)
@@ -279,7 +368,6 @@ def run_gpu_arm(args):
     achieved = mlp_flop / (mlp_ms * 1e-3) / 1e12
 
     if rank == 0:
-        cpu_rps, cpu_secs, cores = cpu_reference_rays_per_s(CPU_SAMPLE_RAYS) if world == 1 else (None, None, None)
         line = {
             "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -287,18 +375,21 @@ def run_gpu_arm(args):
             "config": {"workload": WORKLOAD,
                        "rays_per_step": rays_per_step, "points_per_ray": POINTS_PER_RAY,
                        "weights": "random-init reference architecture (seed 0, alpha bias 0.1)",
+                       "timed_region": "raygen + 8-launch render of the rank's shard + all-gather, poses resident in HBM",
                        "l2": "per-step working set 1.6 GB (raw_fine alone 0.94 GB) >> 126 MB L2; no explicit flush"},
             "ms_per_frame": total_ms / args.steps,
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 64 * world,
-                    "d2h_bytes_per_step": 3 * rays_per_step, "ms_per_frame": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "NeRFReplicaInferenceHandler.render_poses"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 64 * world * world,
+                    "d2h_bytes_per_step": 3 * rays_per_step * world, "ms_per_frame": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "bytes_note": "summed over ranks: every rank uploads the batch's poses and reads back the gathered frames",
+                    "api": "NeRFReplicaInferenceHandler.render_poses" if world == 1 else
+                           "nwx.dist.render_poses_sharded(handler, poses, to_host=True)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": mlp_dram_traffic_per_step(),
-                         "traffic_note": "DRAM bytes of the step's two launches: ncu --set full of the fine launch "
-                                         "(profiles/r01_ncu_mlp_full_fold.csv, 1.32 GB) scaled by points; "
-                                         "algorithmic: 20 B/point + 556 B/ray = 1.74 GB",
+                         "traffic_note": "STATIC, not measured in this run: DRAM bytes of the step's two launches from the "
+                                         "committed ncu --set full capture of the fine launch (" + NCU_MLP_CAPTURE + "), scaled "
+                                         "by points; algorithmic: 20 B/point + 556 B/ray = 1.74 GB",
                          "kernel": "mlp_fused_kernel (2 launches/step)",
                          "peak_source": peak_src, "flop_per_step": mlp_flop, "kernel_ms_per_step": mlp_ms,
                          "executed": achieved * FLOP_PER_POINT_EXECUTED / FLOP_PER_POINT,
@@ -307,14 +398,136 @@ def run_gpu_arm(args):
                                  "the kernel executes 11.5 % fewer (feature layer folded into the views layer at weight "
                                  "load, exact algebra) -- executed/frac_executed is the tensor-pipe view"},
             "stages_ms": {k: mean(k) for k in E.Engine.STAGES},
+            "strong": strong,
+            "train": train,
         }
-        if cpu_rps is not None:
+        if world == 1:
+            line["function_level"] = function_level_bench(nwx, handler, dev, sd_c, sd_f, poses_dev)
+            eager_ms, eager_img = gpu_eager_frame_ms(dev)
+            mine = handler.render_poses(pinned_one)[0]
+            line["gpu_eager_baseline"] = {
+                "value": H * W / (eager_ms * 1e-3), "unit": "rays/s", "ms_per_frame": eager_ms, "kind": "port",
+                "what": "the reference's GPU path: torch eager fp32 (TF32 off), CPU raygen + H2D, 8192-ray chunks x "
+                        "32768-point network chunks, D2H + to8b_np -- the oracle port with CUDA tensors, one 640x480 frame",
+                "speedup_e2e": eager_ms / (e2e_ms / e2e_steps),
+                "max_abs_uint8_diff_vs_nwx": int(abs(eager_img.astype(int) - mine.astype(int)).max())}
+            cpu_rps, cpu_secs, cores = cpu_reference_rays_per_s(CPU_SAMPLE_RAYS)
+            an_rps, an_secs, _ = cpu_reference_rays_per_s(4096, anomaly=True, warm=64)
             line["cpu_baseline"] = {"value": cpu_rps, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"{CPU_SAMPLE_RAYS} rays strided over the same 640x480 view "
-                                              f"({cpu_secs:.1f} s of CPU work)"}
+                                              f"({cpu_secs:.1f} s of CPU work); same work per ray as BASELINE config 1 "
+                                              "(160x120), chunk 8192 / net_chunk 32768, anomaly detection off",
+                                    "anomaly_on_value": an_rps,
+                                    "anomaly_on_sample": f"4096 rays, torch.autograd.set_detect_anomaly(True) as the "
+                                                         f"reference ships it ({an_secs:.1f} s)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def function_level_bench(nwx, handler, dev, sd_c, sd_f, poses_dev):
+    """The reference handler's OWN call sequence (inference handler:187-277: batchify_rays over 8192-ray chunks,
+    run_network with the lambda, raw2outputs, sample_pdf, torch.sort) on nwx's function-level entry points."""
+    from nwx import engine as E
+    from nwx.reference_patch import ReferenceStyleRenderer
+    r = ReferenceStyleRenderer(sd_c, sd_f, dev)
+    rays = handler.engine.raygen(poses_dev[:1], H, W, handler._fx, handler._fy, handler._cx, handler._cy, NEAR, FAR, True)
+    chunk = 8192
+
+    def frame():
+        out = nwx.batchify_rays(r._volumetric_rendering, rays, chunk)
+        return nwx.to8b(out["rgb_fine"])
+    frame()
+    torch.cuda.synchronize()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 3
+    e0.record()
+    for _ in range(steps):
+        img = frame()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fused = handler.render_rays_u8(poses_dev[:1], 0, H * W)
+    return {"ms_per_frame": ms, "rays_per_s": H * W / (ms * 1e-3), "chunk": chunk,
+            "nwx_launches_per_frame": (E.launch_count() - l0) / steps,
+            "max_abs_uint8_diff_vs_fused_sequence": int((img.int() - fused.int()).abs().max()),
+            "what": "reference-shaped handler code (38 chunks of 8192 rays, 11-key dict per chunk, torch cat/sort glue) "
+                    "calling nwx.run_network / raw2outputs / sample_pdf; both run_network calls resolve to the fused kernel"}
+
+
+def run_train_bench(nwx, dev, world, rank, barrier, args):
+    """BASELINE configs[3]: NeRFReplicaTrainingHandler.step with 4096 rays per GPU on synthetic Replica-shaped banks
+    ([180, 76800, 11] rays, U[0,1] pixels), data-parallel gradient all-reduce over NCCL (training handler:265-339)."""
+    import torch.distributed as dist
+    from nwx import engine as E
+    from nwx import synthetic
+    n_img, h, w = TRAIN_BANK
+    fx, fy, cx, cy = synthetic.intrinsics(h, w)
+    bank_eng = nwx.Engine(dev)
+    poses = synthetic.sweep_poses(36, 0).repeat(n_img // 36, 1, 1)[:n_img]
+    bank = bank_eng.raygen(poses, h, w, fx, fy, cx, cy, NEAR, FAR).view(n_img, h * w, 11)
+    rgbs = torch.rand((n_img, h * w, 3), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    cfg = nwx.config.default_config()
+    cfg["rendering"]["n_rays"] = TRAIN_RAYS_PER_GPU
+    cfg["experiment"].update(image_height=h, image_width=w)
+    th = nwx.NeRFReplicaTrainingHandler("office_tokyo", cfg, bank, rgbs, *synthetic.random_state_dicts(0), device=dev, seed=2)
+    warm, steps = 5, max(20, min(5 * args.steps, 100))
+    for i in range(warm):
+        th.step(i)
+    barrier()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = th.step(warm + i)
+    e1.record()
+    barrier()
+    launches = (E.launch_count() - l0) / steps
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    # the all-reduce alone (both networks' gradients, 4.77 MB) for the record
+    ar_ms = 0.0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        g = th.trainer.grads.clone()
+        for _ in range(5):
+            dist.all_reduce(g)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(g)
+        a1.record()
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / 20
+    # data-parallel invariants: identical parameters everywhere, different batches per rank
+    same, differ = True, True
+    if world > 1:
+        chk = th.trainer.params.double().sum().reshape(1)
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        same = all(bool(torch.equal(c, allc[0])) for c in allc)
+        idx = th._sample_training_data(want_indices=True)[2][:64].contiguous()
+        alli = [torch.empty_like(idx) for _ in range(world)]
+        dist.all_gather(alli, idx)
+        differ = all(not torch.equal(alli[0], a) for a in alli[1:])
+    ms_step = float(ms)
+    pts = TRAIN_RAYS_PER_GPU * POINTS_PER_RAY
+    peak, _ = measured_peak_tflops()
+    hbm_peak = measured_hbm_gbs()
+    tflops = FLOP_PER_POINT_TRAIN * pts / (ms_step * 1e-3) / 1e12
+    gbs = TRAIN_BYTES_PER_POINT * pts / (ms_step * 1e-3) / 1e9
+    return {"workload": f"NeRFReplicaTrainingHandler.step: {TRAIN_RAYS_PER_GPU} rays/GPU sampled on device from "
+                        f"[{n_img},{h * w},11] banks, 64+128 samples, jitter + noise + random u in-kernel, MSE coarse+fine, "
+                        "fused backward, grad all-reduce (coarse half overlapped with the fine backward), Adam, LR decay",
+            "n_gpus": world, "ms_per_step": ms_step, "rays_per_s": world * TRAIN_RAYS_PER_GPU / (ms_step * 1e-3), "steps": steps,
+            "tflops_per_gpu": tflops, "frac_of_sustained_bf16": tflops / peak,
+            "hbm_gbs_per_gpu": gbs, "frac_of_hbm": gbs / hbm_peak,
+            "bytes_per_point_model": TRAIN_BYTES_PER_POINT, "flop_per_point": FLOP_PER_POINT_TRAIN,
+            "allreduce_ms_alone": ar_ms, "allreduce_bytes": 2 * 595844 * 4,
+            "kernel_launches_per_step": launches, "host_syncs_per_step": 0,
+            "params_identical_across_ranks": same, "batches_differ_across_ranks": differ,
+            "loss": [float(out["rgb_loss_coarse"]), float(out["rgb_loss_fine"])]}
 
 
 def main():

@@ -63,8 +63,13 @@ class Trainer:
                  lr: float = 5e-4, lr_decay_rate: float = 0.1, lr_decay_steps: int = 50000,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, n_samples: int = 64,
                  n_importance: int = 128, white_bkgd: bool = False, perturb: float = 1.0, raw_noise_std: float = 1.0,
-                 group: Optional[dist.ProcessGroup] = None, seed: int = 0, overlap_allreduce: bool = True):
+                 group: Optional[dist.ProcessGroup] = None, seed: int = 0, overlap_allreduce: bool = True,
+                 data_parallel: bool = True):
+        """`group`: the data-parallel process group (None = the default group when torch.distributed is
+        initialised).  data_parallel=False keeps this trainer local even under torch.distributed (no collectives,
+        unshifted seed) -- e.g. a single-rank reference run inside a multi-rank job."""
         self.engine, self.device, self.group = eng, eng.device, group
+        self.data_parallel = bool(data_parallel)
         self.lr0, self.lr, self.lr_decay_rate, self.lr_decay_steps = lr, lr, lr_decay_rate, lr_decay_steps
         self.betas, self.eps = betas, eps
         self.n_samples, self.n_importance, self.white_bkgd = n_samples, n_importance, white_bkgd
@@ -80,8 +85,8 @@ class Trainer:
         self.loss = torch.zeros(2, device=self.device, dtype=torch.float64)
         self.opt_steps = 0
         # in-kernel RNG key (rank-folded: each rank draws its own jitter / u / noise / pixels) and per-call offset
-        self.base_seed, self.seed, self.draws = int(seed), rank_seed(seed, group), 0
-        self.world = world_of(group)
+        self.base_seed, self.seed, self.draws = int(seed), (rank_seed(seed, group) if self.data_parallel else int(seed)), 0
+        self.world = world_of(group) if self.data_parallel else 1
         if self.world > 1:
             # identical parameters on every rank regardless of what each rank was constructed with
             dist.broadcast(self.params, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
@@ -209,12 +214,19 @@ class Trainer:
         """All-reduce (mean) the gradients across ranks, Adam, re-pack, then the reference's
         learning-rate schedule lr = lr0 * rate^(step/decay_steps) (training handler:312-315),
         which -- as in the reference -- takes effect from the NEXT step."""
-        if self._coarse_reduced:                                      # coarse half already in flight on the side stream
+        if not self.data_parallel:
+            scale = 1.0
+        elif self._coarse_reduced:                                    # coarse half already in flight on the side stream
             scale = allreduce_sum_(self.grads[FINE], self.group)     # 2.38 MB
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
             self._coarse_reduced = False
         else:
             scale = allreduce_sum_(self.grads, self.group)           # 4.77 MB, one NCCL call
+        self.apply_optimizer(global_step, scale)
+
+    def apply_optimizer(self, global_step: int, grad_scale: float = 1.0) -> None:
+        """Adam on self.grads * grad_scale, re-pack, learning-rate schedule (the local part of optimizer_step)."""
+        scale = grad_scale
         self.opt_steps += 1
         n = self.params.numel()
         check(self.engine._lib.nwx_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),

@@ -18,6 +18,12 @@ those fixtures wherever the tests run (the reference itself does not travel).
 Every function cites the reference file:line it follows.  The arithmetic is kept
 op-for-op identical (same torch ops in the same order, fp32) because bit-exact
 ray / searchsorted indices are part of the parity contract.
+
+The render / training functions follow the device of their inputs (constants are created where
+the reference creates them -- on the CPU -- and moved like its ``.cuda()`` calls do): with CPU
+tensors this is the pinned oracle; with CUDA tensors it is what the reference executes on a GPU
+(torch eager, fp32), used as the ``gpu_eager_baseline`` of bench.py and as the fp32 training
+reference of tests/test_gpu_trained.py.  CUDA results are NOT bit-pinned (cuBLAS / CUB orders).
 """
 from __future__ import annotations
 
@@ -100,10 +106,10 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, det: b
     cdf = pdf_to_cdf(weights)
     if u is None:
         if det:
-            u = torch.linspace(0., 1., steps=n_samples)                          # rays.py:95
+            u = torch.linspace(0., 1., steps=n_samples).to(cdf.device)           # rays.py:95 (+ .cuda() :100)
             u = u.expand(list(cdf.shape[:-1]) + [n_samples])
         else:
-            u = torch.rand(list(cdf.shape[:-1]) + [n_samples])                   # rays.py:98
+            u = torch.rand(list(cdf.shape[:-1]) + [n_samples]).to(cdf.device)    # rays.py:98
     samples, inds = invert_cdf(bins, cdf, u)
     return (samples, inds) if return_inds else samples
 
@@ -260,13 +266,13 @@ def raw2outputs(raw: torch.Tensor, z_vals: torch.Tensor, rays_d: torch.Tensor, r
 
     ``noise`` injects the N(0,1)*std draw of model_utils.py:65 (already scaled)."""
     dists = z_vals[..., 1:] - z_vals[..., :-1]                                   # :51
-    dists = torch.cat([dists, torch.Tensor([1e10]).expand(dists[..., :1].shape)], -1)   # :56
+    dists = torch.cat([dists, torch.full_like(dists[..., :1], 1e10)], -1)        # :56 (Tensor([1e10]).expand)
     dists = dists * torch.norm(rays_d[..., None, :], dim=-1)                     # :60
     rgb = torch.sigmoid(raw[..., :3])                                            # :62
     if noise is None:
-        noise = torch.randn(raw[..., 3].shape) * raw_noise_std if raw_noise_std > 0. else 0.
+        noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std if raw_noise_std > 0. else 0.
     alpha = 1. - torch.exp(-torch.relu(raw[..., 3] + noise) * dists)             # :49,:71
-    trans = torch.cumprod(torch.cat([torch.ones((alpha.shape[0], 1)), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], -1), -1)[:, :-1]   # :73-77
     weights = alpha * trans                                                      # :79-80
     rgb_map = torch.sum(weights[..., None] * rgb, -2)                            # :84
     depth_map = torch.sum(weights * z_vals, -1)                                  # :93
@@ -301,7 +307,7 @@ def coarse_z(ray_batch: torch.Tensor, n_samples: int, t_rand: Optional[torch.Ten
     inference handler:213-220; training handler:544-562 (t_rand = the torch.rand of :560)."""
     bounds = torch.reshape(ray_batch[..., 6:8], [-1, 1, 2])
     near, far = bounds[..., 0], bounds[..., 1]
-    t_vals = torch.linspace(0., 1., steps=n_samples)
+    t_vals = torch.linspace(0., 1., steps=n_samples).to(ray_batch.device)       # computed on the CPU, then .cuda() (:216)
     z = near * (1. - t_vals) + far * t_vals
     z = z.expand([ray_batch.shape[0], n_samples])
     if t_rand is not None:
