@@ -14,7 +14,10 @@
 // (ATen cpu_cum_base_kernel, acc_type<float,false>), so the scan runs in fp64 as well: the
 // transmittance then matches the reference bit for bit except where a 1e-16 relative
 // difference in the double product straddles an fp32 rounding boundary.
-#include "nwx_common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+#include "mlp_device.cuh"   // mbarrier / bulk-copy wrappers and the bounded barrier wait
 
 namespace nwx {
 
@@ -112,8 +115,84 @@ __device__ __forceinline__ float ray_dnorm(const float* __restrict__ rays_d, int
 
 // Forward.  Lane-contiguous layout: lane l owns the K consecutive samples [l*K, l*K + K) of the ray, so the
 // per-sample chain (dist -> alpha -> local transmittance product) is lane-local and ONE fp64 warp scan per ray
-// (over the lanes' products) replaces one scan per 32-sample chunk; the lanes' K x 16 B runs tile the ray's
-// contiguous [S,4] block, so every fetched sector is used (through L1).
+// (over the lanes' products) replaces one scan per 32-sample chunk.
+//
+// Two front ends feed the same arithmetic (composite_ray):
+//   * bulk (default): the ray's contiguous [S,4] raw block and its S depths are brought into shared memory by TWO
+//     1-D TMA bulk copies per ray (cp.async.bulk + mbarrier complete_tx, issued by lane 0), and the lanes read their
+//     K x 16 B runs with LDS.128.  The next ray's copies are issued as soon as the registers are loaded, so they
+//     fly underneath this ray's math.  HBM sees perfectly linear 3 KB + 768 B requests and the LSU no strided
+//     global wavefronts: the direct version below needs 32 L1 wavefronts per LDG.128 (each lane in its own
+//     128-byte line) -- ~210 per fine ray, which is what bounded it at 0.37 ms per frame.
+//   * direct: per-lane __ldg of the same runs (any alignment, any S); also the A/B baseline (NWX_COMPOSITE=direct).
+template <int K>
+__device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float (&zr)[K + 1], const float (&nz)[K], bool noisy,
+                                              int64_t ray, int S, int lane, const float* __restrict__ rays_d, int d_stride,
+                                              int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
+                                              float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
+                                              uint8_t* __restrict__ rgb8, int& bad) {
+  const int s0 = lane * K;
+  const int64_t base = ray * S;
+  const float dnorm = ray_dnorm(rays_d, d_stride, ray);
+  float alpha[K];
+  double tloc[K];                                             // product of t over my samples before j
+  double p = 1.0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int s = s0 + j;
+    float dist = (s >= S - 1) ? 1e10f : __fsub_rn(zr[j + 1], zr[j]);       // :51,:56
+    dist = __fmul_rn(dist, dnorm);                                        // :60
+    const float sg = noisy ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
+    float a = __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg, 0.0f), dist)));   // :49
+    float t = __fadd_rn(__fsub_rn(1.0f, a), 1e-10f);                      // :75
+    if (s >= S) { a = 0.0f; t = 1.0f; }                                   // padding samples: neutral
+    alpha[j] = a;
+    tloc[j] = p;
+    p *= (double)t;
+  }
+  const double incl = warp_incl_prod(p, lane);                // :75 cumprod (exclusive), fp64 like torch
+  double excl = __shfl_up_sync(kFull, incl, 1);
+  if (lane == 0) excl = 1.0;
+  float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int s = s0 + j;
+    const float T = (float)(excl * tloc[j]);
+    const float w = __fmul_rn(alpha[j], T);
+    if (s < S) {
+      if (weights) weights[base + s] = w;
+      a_r += __fmul_rn(w, sigmoidf_fast(rw[j].x));                        // :62,:84
+      a_g += __fmul_rn(w, sigmoidf_fast(rw[j].y));
+      a_b += __fmul_rn(w, sigmoidf_fast(rw[j].z));
+      a_d += __fmul_rn(w, zr[j]);
+      a_w += w;
+    }
+  }
+  a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);        // :84
+  a_d = warp_sum(a_d); a_w = warp_sum(a_w);                             // :93,:95
+  if (lane == 0) {
+    const float q = __fdiv_rn(a_d, a_w);                               // :94; 0/0 = NaN on empty rays and
+    const float dspv = __fdiv_rn(1.0f, (q != q) ? q : fmaxf(1e-10f, q));   // torch.max propagates NaN
+    if (white_bkgd) {                                                   // :98
+      const float bg = __fsub_rn(1.0f, a_w);
+      a_r = __fadd_rn(a_r, bg); a_g = __fadd_rn(a_g, bg); a_b = __fadd_rn(a_b, bg);
+    }
+    if (rgb) { rgb[ray * 3 + 0] = a_r; rgb[ray * 3 + 1] = a_g; rgb[ray * 3 + 2] = a_b; }
+    if (rgb8) {                                                         // to8b_np, model_utils.py:9
+      rgb8[ray * 3 + 0] = to8b_one(a_r); rgb8[ray * 3 + 1] = to8b_one(a_g); rgb8[ray * 3 + 2] = to8b_one(a_b);
+    }
+    if (disp) disp[ray] = dspv;
+    if (acc) acc[ray] = a_w;
+    if (depth) depth[ray] = a_d;
+    const float chk[6] = {a_r, a_g, a_b, dspv, a_w, a_d};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      if (chk[c] != chk[c]) bad |= 1;
+      else if (fabsf(chk[c]) == INFINITY) bad |= 2;
+    }
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kCompWarps * 32, 4)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
@@ -140,66 +219,77 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       nz[j] = noise ? __ldg(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
     }
     zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // z of the sample after my last one
-    const float dnorm = ray_dnorm(rays_d, d_stride, ray);
-    float alpha[K];
-    double tloc[K];                                             // product of t over my samples before j
-    double p = 1.0;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int s = s0 + j;
-      float dist = (s >= S - 1) ? 1e10f : __fsub_rn(zr[j + 1], zr[j]);       // :51,:56
-      dist = __fmul_rn(dist, dnorm);                                        // :60
-      const float sg = noisy ? __fadd_rn(rw[j].w, nz[j]) : rw[j].w;          // :71
-      float a = __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg, 0.0f), dist)));   // :49
-      float t = __fadd_rn(__fsub_rn(1.0f, a), 1e-10f);                      // :75
-      if (s >= S) { a = 0.0f; t = 1.0f; }                                   // padding samples: neutral
-      alpha[j] = a;
-      tloc[j] = p;
-      p *= (double)t;
-    }
-    const double incl = warp_incl_prod(p, lane);                // :75 cumprod (exclusive), fp64 like torch
-    double excl = __shfl_up_sync(kFull, incl, 1);
-    if (lane == 0) excl = 1.0;
-    float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int s = s0 + j;
-      const float T = (float)(excl * tloc[j]);
-      const float w = __fmul_rn(alpha[j], T);
-      if (s < S) {
-        if (weights) weights[base + s] = w;
-        a_r += __fmul_rn(w, sigmoidf_fast(rw[j].x));                        // :62,:84
-        a_g += __fmul_rn(w, sigmoidf_fast(rw[j].y));
-        a_b += __fmul_rn(w, sigmoidf_fast(rw[j].z));
-        a_d += __fmul_rn(w, zr[j]);
-        a_w += w;
-      }
-    }
-    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);        // :84
-    a_d = warp_sum(a_d); a_w = warp_sum(a_w);                             // :93,:95
-    if (lane == 0) {
-      const float q = __fdiv_rn(a_d, a_w);                               // :94; 0/0 = NaN on empty rays and
-      const float dspv = __fdiv_rn(1.0f, (q != q) ? q : fmaxf(1e-10f, q));   // torch.max propagates NaN
-      if (white_bkgd) {                                                   // :98
-        const float bg = __fsub_rn(1.0f, a_w);
-        a_r = __fadd_rn(a_r, bg); a_g = __fadd_rn(a_g, bg); a_b = __fadd_rn(a_b, bg);
-      }
-      if (rgb) { rgb[ray * 3 + 0] = a_r; rgb[ray * 3 + 1] = a_g; rgb[ray * 3 + 2] = a_b; }
-      if (rgb8) {                                                         // to8b_np, model_utils.py:9
-        rgb8[ray * 3 + 0] = to8b_one(a_r); rgb8[ray * 3 + 1] = to8b_one(a_g); rgb8[ray * 3 + 2] = to8b_one(a_b);
-      }
-      if (disp) disp[ray] = dspv;
-      if (acc) acc[ray] = a_w;
-      if (depth) depth[ray] = a_d;
-      const float chk[6] = {a_r, a_g, a_b, dspv, a_w, a_d};
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        if (chk[c] != chk[c]) bad |= 1;
-        else if (fabsf(chk[c]) == INFINITY) bad |= 2;
-      }
-    }
+    composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, rays_d, d_stride, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad);
   }
   if (flags && bad) atomicOr(flags, bad);
+}
+
+// Bulk front end (see above).  Requires S % 4 == 0 and 16-byte aligned raw / z (the launcher checks).
+template <int K>
+__global__ void __launch_bounds__(kCompWarps * 32, 4)
+composite_fwd_bulk_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                          const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
+                          const RngSpec rng, int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
+                          float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
+                          int32_t* __restrict__ flags, uint8_t* __restrict__ rgb8) {
+  __shared__ __align__(128) float4 s_raw[kCompWarps][K * 32];
+  __shared__ __align__(16) float s_z[kCompWarps][K * 32];
+  __shared__ __align__(8) uint64_t s_bar[kCompWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const bool noisy = noise != nullptr || rng.on;
+  const int s0 = lane * K;
+  const uint32_t bar = smem_u32(&s_bar[wib]), dst_raw = smem_u32(&s_raw[wib][0]), dst_z = smem_u32(&s_z[wib][0]);
+  const uint32_t raw_bytes = (uint32_t)S * 16u, z_bytes = (uint32_t)S * 4u;
+  const WaitCtx wc{nullptr, 0x5100u};
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  auto fetch = [&](int64_t ray) {                               // lane 0: two linear bulk copies, one barrier phase
+    mbar_arrive_expect_tx(bar, raw_bytes + z_bytes);
+    bulk_g2s(dst_raw, raw + ray * S * 4, raw_bytes, bar);
+    bulk_g2s(dst_z, z + ray * S, z_bytes, bar);
+  };
+  if (warp0 < N && lane == 0) fetch(warp0);
+  uint32_t phase = 0;
+  int bad = 0;
+  for (int64_t ray = warp0; ray < N; ray += nwarps) {
+    const int64_t base = ray * S;
+    float zr[K + 1], nz[K];
+    float4 rw[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {                               // the noise (training) does not go through smem
+      const int s = s0 + j;
+      const int64_t idx = base + (s < S ? s : S - 1);
+      nz[j] = noise ? __ldg(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
+    }
+    mbar_wait(bar, phase, wc);
+    phase ^= 1u;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int s = s0 + j, sc = s < S ? s : S - 1;
+      rw[j] = s_raw[wib][sc];
+      zr[j] = s_z[wib][sc];
+    }
+    zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // z of the sample after my last one
+    __syncwarp();                                               // every lane has its registers: the buffer is free
+    if (lane == 0 && ray + nwarps < N) fetch(ray + nwarps);     // next ray's bytes fly underneath this ray's math
+    composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, rays_d, d_stride, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad);
+  }
+  if (flags && bad) atomicOr(flags, bad);
+}
+
+// NWX_COMPOSITE=direct forces the per-lane global loads (A/B measurements)
+static bool composite_bulk_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("NWX_COMPOSITE");
+    on = (e && strcmp(e, "direct") == 0) ? 0 : 1;
+  }
+  return on == 1;
 }
 
 // Backward: d(loss)/d(raw) from d(loss)/d(rgb_map).  With w_i = alpha_i T_i, T_i = prod_{j<i} t_j,
@@ -283,8 +373,15 @@ int nwx::launch_composite_fwd(const float* raw, const float* z, const float* ray
   NWX_REQUIRE(d_stride >= 3 && S >= 1 && S <= 256 && N >= 0);
   if (N == 0) return NWX_OK;
   NWX_REQUIRE(raw && z && rays_d && (rgb || rgb8));
-  NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
-                        raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8)));
+  const bool bulk = nwx::composite_bulk_enabled() && (S % 4) == 0 && ((reinterpret_cast<uintptr_t>(raw) & 15u) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
+  if (bulk) {
+    NWX_DISPATCH_K(S, (nwx::composite_fwd_bulk_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
+                          raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8)));
+  } else {
+    NWX_DISPATCH_K(S, (nwx::composite_fwd_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
+                          raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8)));
+  }
   NWX_LAUNCHED();
   return NWX_OK;
 }

@@ -270,7 +270,7 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   float* z_c = out->z_vals_coarse ? out->z_vals_coarse : s + pl.z_c;
   float* raw_c = out->raw_coarse ? out->raw_coarse : s + pl.raw_c;
   float* w_c = out->weights_coarse ? out->weights_coarse : s + pl.w_c;
-  float* z_s = out->z_samples ? out->z_samples : s + pl.z_s;
+  float* z_s = out->z_samples;                       // NULL = not wanted: the resampling kernel then skips the store
   float* z_f = out->z_vals_fine ? out->z_vals_fine : s + pl.z_f;
   float* raw_f = out->raw_fine ? out->raw_fine : s + pl.raw_f;
   float* rgb_c = out->rgb_coarse ? out->rgb_coarse : s + pl.rgb_c;
@@ -294,7 +294,8 @@ extern "C" int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const
   if ((rc = nwx::launch_composite_fwd(raw_c, z_c, rays + 3, rd, o->noise_coarse, rnc, N, Sc, o->white_bkgd, rgb_c,
                                       out->disp_coarse, out->acc_coarse, out->depth_coarse, w_c, out->flags, st))) return rc;
   if ((rc = mark(4))) return rc;
-  if ((rc = nwx::launch_sample_pdf(z_c, w_c, Sc, o->u, ru, o->u_lin, Ni, N, z_s, z_f, out->inds, out->z_std, st))) return rc;
+  if ((rc = nwx::launch_sample_pdf(z_c, w_c, Sc, o->u, ru, o->u_lin, Ni, N, z_s, z_f, out->inds, out->z_std, st,
+                                   s + pl.z_s))) return rc;
   if ((rc = mark(5))) return rc;
   if ((rc = run_mlp(ctx, NWX_NET_FINE, rays, rd, z_f, nullptr, rays + 8, rd, N, N * Sf, Sf, dirb, raw_f, st, nullptr,
                     prof ? ctx->ev[6] : nullptr))) return rc;

@@ -87,7 +87,8 @@ int launch_composite_bwd(const float* raw, const float* z, const float* rays_d, 
                          const RngSpec& rng, const float* d_rgb, int64_t N, int S, int white_bkgd, float* d_raw,
                          cudaStream_t st);
 int launch_sample_pdf(const float* z_c, const float* w_c, int Sc, const float* u, const RngSpec& rng, const float* u_lin,
-                      int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds, float* z_std, cudaStream_t st);
+                      int n_imp, int64_t N, float* z_samples, float* z_fine, int64_t* inds, float* z_std, cudaStream_t st,
+                      float* z_samples_scratch = nullptr);   // z_samples == NULL: not wanted (scratch for kernels that need it)
 
 // Embedding.embed on rows of stride x_stride (rays.cu)
 int launch_embed(const float* x, int x_stride, int64_t P, int num_freqs, float scalar_factor, float* out,

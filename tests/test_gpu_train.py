@@ -200,7 +200,9 @@ def test_checkpoint_round_trip_reference_format(tmp_path):
     path = str(tmp_path / "000002.ckpt")
     tr.save_checkpoint(path, 2)
     ckpt = torch.load(path)
-    assert set(ckpt) == {"global_step", "network_coarse_state_dict", "network_fine_state_dict", "optimizer_state_dict"}
+    # the reference's four keys (training handler:404-407) + the trainer's RNG state (ignored by the reference's loaders)
+    assert set(ckpt) == {"global_step", "network_coarse_state_dict", "network_fine_state_dict", "optimizer_state_dict",
+                         "nwx_rng"}
     params = [torch.nn.Parameter(v.clone()) for sd in (ckpt["network_coarse_state_dict"], ckpt["network_fine_state_dict"])
               for v in sd.values()]
     torch.optim.Adam(params, lr=5e-4).load_state_dict(ckpt["optimizer_state_dict"])      # the reference's optimizer
