@@ -168,6 +168,11 @@ typedef struct nwx_render_out {       /* any pointer may be NULL = not wanted; o
  * which allocates). */
 int nwx_ctx_reserve(nwx_ctx* ctx, int64_t max_rays, int n_samples, int n_importance);
 
+/* Size of the context's scratch and a generation counter that changes whenever it is re-allocated.  A caller that
+ * captures nwx_render_rays into a CUDA graph (the graph bakes in the scratch address and the biases, which ride in
+ * the kernel parameters) must re-capture when the generation changed or nwx_load_weights ran. */
+int nwx_ctx_scratch_state(nwx_ctx* ctx, int64_t* bytes /* host */, int64_t* generation /* host */);
+
 /* inference handler:203-277 / training handler:534-618 for N rays [N,ray_dim]. */
 int nwx_render_rays(nwx_ctx* ctx, const float* rays, int64_t N, const nwx_render_opts* opts,
                     const nwx_render_out* out, void* stream);

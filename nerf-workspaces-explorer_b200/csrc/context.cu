@@ -23,6 +23,7 @@ struct nwx_ctx {
   // scratch, grown on demand (nwx_ctx_reserve pre-sizes it)
   float* scratch = nullptr;
   size_t scratch_floats = 0;
+  int64_t scratch_generation = 0;   // bumped whenever the scratch is re-allocated (captured CUDA graphs hold its address)
   float* dbg_out = nullptr;      // optional tap target set by nwx_debug_tap
   int dbg_layer = -1;
   uint32_t* diag = nullptr;      // host-mapped diagnostics the kernels write before aborting (own_diag unless overridden)
@@ -80,6 +81,7 @@ int ensure_scratch(nwx_ctx* ctx, size_t floats) {
   ctx->scratch_floats = 0;
   NWX_CUDA_TRY(cudaMalloc(&ctx->scratch, floats * sizeof(float)));
   ctx->scratch_floats = floats;
+  ++ctx->scratch_generation;
   return NWX_OK;
 }
 
@@ -191,6 +193,13 @@ extern "C" int nwx_ctx_stage_ms(nwx_ctx* ctx, float* ms_out) {
   NWX_REQUIRE(ctx && ms_out && ctx->ev_recorded);
   NWX_CUDA_TRY(cudaEventSynchronize(ctx->ev[NWX_NUM_STAGES]));
   for (int i = 0; i < NWX_NUM_STAGES; ++i) NWX_CUDA_TRY(cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
+  return NWX_OK;
+}
+
+extern "C" int nwx_ctx_scratch_state(nwx_ctx* ctx, int64_t* bytes, int64_t* generation) {
+  NWX_REQUIRE(ctx && bytes && generation);
+  *bytes = (int64_t)(ctx->scratch_floats * sizeof(float));
+  *generation = ctx->scratch_generation;
   return NWX_OK;
 }
 

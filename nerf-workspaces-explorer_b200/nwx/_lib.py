@@ -58,6 +58,7 @@ PROTOTYPES = {
     "nwx_sample_pdf": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nwx_sample_pdf_bins": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "nwx_ctx_reserve": (_i, [_vp, _i64, _i, _i]),
+    "nwx_ctx_scratch_state": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "nwx_param_offsets": (_i, [C.POINTER(_i)]),
     "nwx_train_pack": (_i, [_vp, _i, _vp, _vp]),
     "nwx_train_fwd_bwd": (_i, [_vp, C.POINTER(TrainIO), _i64, C.POINTER(RenderOpts), _vp]),

@@ -54,9 +54,8 @@ def render_poses_sharded(handler, c2w: torch.Tensor, group: Optional[dist.Proces
     eng = handler.engine
     H, W = handler._img_h, handler._img_w
     B = c2w.shape[0]
-    c2w_dev = c2w.to(eng.device, dtype=torch.float32, non_blocking=True)
     with torch.no_grad():
-        full = render_sharded(B * H * W, lambda start, count: handler.render_rays_u8(c2w_dev, start, count), group)
+        full = render_sharded(B * H * W, lambda start, count: handler.render_rays_u8(c2w, start, count), group)
     if to_host:
         return handler.frames_to_host(full, B)
     return full.view(B, H, W, 3)

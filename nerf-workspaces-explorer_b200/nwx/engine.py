@@ -125,6 +125,8 @@ class Engine:
         check(self._lib.nwx_ctx_create(self.device.index or 0, C.byref(handle)), "nwx_ctx_create")
         self._ctx = handle
         self._keep = {}
+        self.weights_version = 0          # bumped by load_weights: captured graphs bake the biases in
+        self.profiling = False
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -145,6 +147,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self._lib.nwx_load_weights(self._ctx, which, arr, _stream()), "nwx_load_weights")
         self._keep[which] = tensors
+        self.weights_version += 1
 
     def set_mlp_variant(self, variant: int) -> None:
         check(self._lib.nwx_set_mlp_variant(self._ctx, variant), "nwx_set_mlp_variant")
@@ -167,6 +170,13 @@ class Engine:
 
     def set_profiling(self, on: bool) -> None:
         check(self._lib.nwx_ctx_set_profiling(self._ctx, int(on)), "nwx_ctx_set_profiling")
+        self.profiling = bool(on)
+
+    def scratch_state(self) -> Tuple[int, int]:
+        """(bytes, generation) of the context's scratch; the generation changes when it is re-allocated."""
+        b, g = C.c_int64(), C.c_int64()
+        check(self._lib.nwx_ctx_scratch_state(self._ctx, C.byref(b), C.byref(g)), "nwx_ctx_scratch_state")
+        return int(b.value), int(g.value)
 
     def stage_ms(self) -> Dict[str, float]:
         """Device time of each stage of the last render_rays call (waits for it)."""
@@ -372,5 +382,15 @@ def to8b(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_GRAPH_LAUNCHES = 0        # kernels launched by CUDA-graph replays (the library only sees the capture)
+
+
+def count_graph_launches(n: int) -> None:
+    global _GRAPH_LAUNCHES
+    _GRAPH_LAUNCHES += int(n)
+
+
 def launch_count() -> int:
-    return int(_lib.lib().nwx_launch_count())
+    """Kernels of libnwx launched so far by this process: direct launches (counted by the library) plus the
+    kernel nodes of every CUDA-graph replay (counted here)."""
+    return int(_lib.lib().nwx_launch_count()) + _GRAPH_LAUNCHES

@@ -21,6 +21,36 @@ from .data_descriptors import COORD
 from .models import Embedding, NeRFModel
 
 
+class _FrameGraph:
+    """The launch sequence of one fixed ray range (raygen + the 8-launch render, uint8 out) captured ONCE into a
+    CUDA graph and replayed: one graph launch per frame instead of a Python -> ctypes -> 9 x cudaLaunch walk, which
+    is what the host adds to a frame once the GPU is drained by the read-back (0.2-0.3 ms, all of it exposed)."""
+
+    def __init__(self, handler: "NeRFReplicaInferenceHandler", B: int, ray0: int, count: int):
+        eng, dev = handler.engine, handler._device
+        self.pose = torch.zeros((B, 4, 4), device=dev, dtype=torch.float32)      # static input
+        self.rgb8 = torch.empty((count, 3), device=dev, dtype=torch.uint8)       # static output
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                   # sizes the scratch, sets the kernels' attributes
+            handler._render_rays_u8_eager(self.pose, ray0, count, self.rgb8)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _engine.launch_count()
+        with torch.cuda.graph(self.graph):
+            handler._render_rays_u8_eager(self.pose, ray0, count, self.rgb8)
+        self.kernels = _engine.launch_count() - before
+        self.stamp = (eng.weights_version, eng.scratch_state()[1])
+
+    def run(self, c2w: torch.Tensor) -> torch.Tensor:
+        self.pose.copy_(c2w, non_blocking=True)          # host (pinned: asynchronous) or device poses
+        self.graph.replay()
+        _engine.count_graph_launches(self.kernels)
+        return self.rgb8
+
+
 class NeRFReplicaInferenceHandler:
 
     def __init__(self, office_name: str, ckpt_path: Optional[str], config: Optional[Mapping] = None,
@@ -61,6 +91,8 @@ class NeRFReplicaInferenceHandler:
         self._embed_fcn = self._embed_dirs_fcn = None
         self.max_rays_per_launch = 1 << 20       # scratch is ~6.4 KB per ray
         self._host_frames: Optional[torch.Tensor] = None     # persistent pinned read-back buffer (uint8)
+        self.use_cuda_graphs = True              # replay a captured launch sequence for repeated frame shapes
+        self._graphs: Dict[Any, _FrameGraph] = {}
 
     @property
     def _device(self) -> torch.device:
@@ -99,6 +131,7 @@ class NeRFReplicaInferenceHandler:
         self._engine = _engine.Engine(self._device)
         self._engine.load_weights(_engine.COARSE, self._nerf_net_coarse.state_dict())
         self._engine.load_weights(_engine.FINE, self._nerf_net_fine.state_dict())
+        self._graphs.clear()                     # captured sequences carry the old biases in their kernel parameters
         # size the scratch for one frame now, so that no render call allocates (or frees) device memory
         self._engine.reserve(max(1, min(self.max_rays_per_launch, self._n_pix)), self._n_samples, self._n_importance)
 
@@ -135,11 +168,29 @@ class NeRFReplicaInferenceHandler:
 
     def render_rays_u8(self, c2w_dev: torch.Tensor, ray0: int, count: int, out: Optional[torch.Tensor] = None
                        ) -> torch.Tensor:
-        """uint8 pixels [count,3] of the rays [ray0, ray0+count) of the B*H*W rays of `c2w_dev` ([B,4,4] on the
-        device): raygen + the 8-launch render, the compositing kernel writes the bytes.  This is the unit the
-        multi-GPU path shards (nwx/dist.py)."""
+        """uint8 pixels [count,3] of the rays [ray0, ray0+count) of the B*H*W rays of the poses `c2w_dev` ([B,4,4],
+        on the device or in host memory): raygen + the 8-launch render, the compositing kernel writes the bytes.  This is the unit the
+        multi-GPU path shards (nwx/dist.py).  Repeated shapes replay a captured CUDA graph (use_cuda_graphs); the
+        returned tensor is then the graph's static output buffer, overwritten by the next call of the same shape."""
         eng = self.engine
+        if (self.use_cuda_graphs and out is None and not eng.profiling and 0 < count <= self.max_rays_per_launch
+                and not torch.cuda.is_current_stream_capturing()):
+            key = (int(c2w_dev.shape[0]), int(ray0), int(count), self._img_h, self._img_w, self._fx, self._fy, self._cx,
+                   self._cy, self._n_samples, self._n_importance, self._white_bkgd)
+            g = self._graphs.get(key)
+            if g is not None and g.stamp != (eng.weights_version, eng.scratch_state()[1]):
+                g = None                              # weights reloaded or scratch re-allocated since the capture
+            if g is None:
+                if len(self._graphs) >= 64:           # e.g. a sweep over many batch sizes: start over
+                    self._graphs.clear()
+                g = self._graphs[key] = _FrameGraph(self, int(c2w_dev.shape[0]), int(ray0), int(count))
+            return g.run(c2w_dev)
         rgb8 = torch.empty((count, 3), device=self._device, dtype=torch.uint8) if out is None else out
+        c2w_dev = c2w_dev.to(self._device, dtype=torch.float32, non_blocking=True)
+        return self._render_rays_u8_eager(c2w_dev, ray0, count, rgb8)
+
+    def _render_rays_u8_eager(self, c2w_dev: torch.Tensor, ray0: int, count: int, rgb8: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
         for s in range(0, count, self.max_rays_per_launch):
             n = min(self.max_rays_per_launch, count - s)
             rays = eng.raygen(c2w_dev, self._img_h, self._img_w, self._fx, self._fy, self._cx, self._cy,
@@ -160,8 +211,7 @@ class NeRFReplicaInferenceHandler:
     def render_poses(self, c2w: torch.Tensor) -> np.ndarray:
         """[B,4,4] camera-to-world poses -> uint8 [B,H,W,3]; H2D 64 B per view, D2H 3 B per pixel."""
         B = c2w.shape[0]
-        c2w_dev = c2w.to(self._device, dtype=torch.float32, non_blocking=True)
-        return self.frames_to_host(self.render_rays_u8(c2w_dev, 0, B * self._n_pix), B)
+        return self.frames_to_host(self.render_rays_u8(c2w, 0, B * self._n_pix), B)
 
     def _render_rays(self, flat_rays: torch.Tensor) -> Dict[str, torch.Tensor]:
         """handler:187-201 -> the 11-key dict for [n,11] rays.  The reference chunks by

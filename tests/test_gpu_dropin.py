@@ -218,3 +218,39 @@ def test_two_training_contexts_on_two_streams_do_not_race():
     torch.cuda.synchronize()
     assert all(torch.equal(x.cpu(), y) for x, y in zip(got_a, la)) and torch.equal(ta.params, pa)
     assert all(torch.equal(x.cpu(), y) for x, y in zip(got_b, lb)) and torch.equal(tb.params, pb)
+
+
+def test_cuda_graph_replay_equals_direct_launches():
+    """render_poses replays a captured launch sequence per frame shape: same bytes as the direct launches for
+    every pose, re-captured when the weights change, counted in launch_count()."""
+    import nwx
+    H, W = 24, 32
+    fx, fy, cx, cy = orc.intrinsics(H, W)
+
+    def make(graphs):
+        h = nwx.NeRFReplicaInferenceHandler("office_tokyo", None)
+        h._img_h, h._img_w, h._n_pix, h._fx, h._fy, h._cx, h._cy = H, W, H * W, fx, fy, cx, cy
+        h.use_cuda_graphs = graphs
+        h.load_state_dicts(*_nets())
+        return h
+    hg, he = make(True), make(False)
+    poses = orc.synthetic_poses(36, 0)
+    for i in (0, 5, 9):
+        a, b = hg.render_poses(poses[i:i + 1]), he.render_poses(poses[i:i + 1])
+        assert np.array_equal(a, b), i
+    assert len(hg._graphs) == 1 and len(he._graphs) == 0
+    before = nwx.engine.launch_count()
+    hg.render_poses(poses[3:4])
+    assert nwx.engine.launch_count() - before == 9                  # replayed kernels are counted
+    two = hg.render_poses(poses[2:4])                                # another shape: another graph
+    assert len(hg._graphs) == 2 and np.array_equal(two, he.render_poses(poses[2:4]))
+    gen = torch.Generator().manual_seed(4)
+    other = (orc.init_state_dict(4, generator=gen), orc.init_state_dict(4, generator=gen))
+    hg.load_state_dicts(*other); he.load_state_dicts(*other)         # new biases: the old graphs must not survive
+    assert len(hg._graphs) == 0
+    c, d = hg.render_poses(poses[5:6]), he.render_poses(poses[5:6])
+    assert np.array_equal(c, d) and not np.array_equal(c, b)
+    # a larger eager render re-allocates the scratch underneath the captured graph: it must notice and re-capture
+    big = hg.engine.raygen(poses[:4], 48, 64, *orc.intrinsics(48, 64), 0.1, 10.0)
+    hg.engine.render_rays(big, want=("rgb_fine",))
+    assert np.array_equal(hg.render_poses(poses[5:6]), d)
