@@ -233,6 +233,14 @@ int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N, const nwx
 int nwx_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* The optimiser step of the training loop in two launches: Adam (as nwx_adam_step) over BOTH networks' flat buffers
+ * -- params / grads / m / v are [2][NWX_PARAMS_PER_NET], coarse then fine -- fused with the re-pack of nwx_train_pack
+ * (the thread that updates a parameter also writes its bf16 / fp32 copies into the kernels' images), then the folded
+ * views layer of both networks.  Needs one nwx_train_pack per network beforehand (allocation, zero padding).  `params`
+ * must stay allocated like params_flat of nwx_train_pack. */
+int nwx_adam_pack_step(nwx_ctx* ctx, float* params, const float* grads, float* m, float* v, float lr, float beta1,
+                       float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* Per-stage device timing of nwx_render_rays (CUDA events on the caller's stream).  Stage order:
  * coarse_z, dirbias(coarse), mlp(coarse), composite(coarse), sample_pdf, dirbias(fine), mlp(fine),
  * composite(fine, incl. the uint8 pixels).  nwx_ctx_stage_ms waits for the last recorded call and fills
@@ -254,6 +262,9 @@ int nwx_set_mlp_variant(nwx_ctx* ctx, int variant);
  * a barrier wait that exceeds its wall-clock bound (10 s) fills before the kernel traps instead of hanging. */
 int nwx_debug_tap(nwx_ctx* ctx, int layer, float* out);
 int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped);
+/* Test hook: copy one packed buffer of network `which` to dst (device, exactly `bytes` long): what = 0 forward weight
+ * image, 1 transposed image (dX), 2 device-side constants, 3 view-direction table, 4 views bias, 5 folded views bias. */
+int nwx_debug_copy_packed(nwx_ctx* ctx, int which, int what, void* dst, int64_t bytes, void* stream);
 /* The 4 diagnostic words (0xDEADxxxx | waiter code, block, barrier, parity) of the last aborted wait; zeros
  * if none.  Every context owns such a host-mapped word from creation (nwx_debug_diag(ctx, NULL) restores
  * it), so the cause of a trap is readable even though the CUDA context is unusable afterwards. */

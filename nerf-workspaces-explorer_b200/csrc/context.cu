@@ -339,6 +339,34 @@ extern "C" int nwx_adam_step(float* params, const float* grads, float* m, float*
   return nwx::launch_adam(params, grads, m, v, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
 }
 
+extern "C" int nwx_adam_pack_step(nwx_ctx* ctx, float* params, const float* grads, float* m, float* v, float lr,
+                                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  NWX_REQUIRE(ctx && params && grads && m && v && step >= 1);
+  return nwx::launch_adam_pack(ctx->net, params, grads, m, v, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+
+// Test hook: copy one packed buffer of a network to `dst` (device): 0 forward weight image, 1 transposed image (dX),
+// 2 device-side constants (biases / heads), 3 view-direction table, 4 views bias, 5 folded views bias.
+extern "C" int nwx_debug_copy_packed(nwx_ctx* ctx, int which, int what, void* dst, int64_t bytes, void* stream) {
+  NWX_REQUIRE(ctx && (which == 0 || which == 1) && dst && bytes >= 0);
+  const nwx::PackedNet& n = ctx->net[which];
+  const void* src = nullptr;
+  int64_t size = 0;
+  switch (what) {
+    case 0: src = n.wimg; size = (int64_t)nwx::kWeightImageBytes; break;
+    case 1: src = n.wimg_t; size = (int64_t)nwx::packed_transposed_bytes(); break;
+    case 2: src = n.gconsts; size = (int64_t)sizeof(nwx::MlpConsts); break;
+    case 3: src = n.wdir_t; size = (int64_t)sizeof(float) * nwx::kPeDir * nwx::kViewHidden; break;
+    case 4: src = n.bview; size = (int64_t)sizeof(float) * nwx::kViewHidden; break;
+    case 5: src = n.bview_fold; size = (int64_t)sizeof(float) * nwx::kViewHidden; break;
+    default: return NWX_E_INVALID;
+  }
+  if (!src) return NWX_E_NO_WEIGHTS;
+  NWX_REQUIRE(bytes == size);
+  NWX_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)size, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return NWX_OK;
+}
+
 namespace {
 // The training kernels read biases / heads from process-global __constant__ banks (mlp.cu c_fwd_train_consts,
 // train.cu c_train_consts) that every nwx_train_fwd_bwd refreshes on its own stream.  Two contexts (or one

@@ -575,10 +575,10 @@ __global__ void pack_dir_kernel(const float* __restrict__ wv, float* __restrict_
 // accumulation, rounded once to fp32 and then to bf16), written as 4 half-size K-block images; and
 // b_fold[j] = b_view[j] + sum_m W_view[j][m] * b_feature[m].  hv = relu(W_fold h8 + b_fold + W_view[:,256:] pe(dir))
 // is the same function as nerf_model.py:64-70 with one bf16 rounding fewer (no rounded `feature`).
-__global__ void pack_fold_kernel(const float* __restrict__ wv, const float* __restrict__ wf,
-                                 const float* __restrict__ bv, const float* __restrict__ bf,
-                                 uint8_t* __restrict__ wimg, float* __restrict__ bview_fold,
-                                 uint8_t* __restrict__ wimg_t /* training: transposed image for dX, or nullptr */) {
+__device__ __forceinline__ void pack_fold_body(const float* __restrict__ wv, const float* __restrict__ wf,
+                                               const float* __restrict__ bv, const float* __restrict__ bf,
+                                               uint8_t* __restrict__ wimg, float* __restrict__ bview_fold,
+                                               uint8_t* __restrict__ wimg_t /* training: transposed image for dX, or nullptr */) {
   const int kb = blockIdx.x;                       // K-block of the folded layer (64 input columns)
   const int n0 = blockIdx.y * 2;                   // 2 output rows per block: 256 blocks, one output per thread
   constexpr int kIn = kHidden + kPeDir;
@@ -607,6 +607,19 @@ __global__ void pack_fold_kernel(const float* __restrict__ wv, const float* __re
     for (int m = 0; m < kHidden; ++m) acc += (double)wv[(size_t)n * kIn + m] * (double)bf[m];
     bview_fold[n] = (float)acc;
   }
+}
+__global__ void pack_fold_kernel(const float* __restrict__ wv, const float* __restrict__ wf,
+                                 const float* __restrict__ bv, const float* __restrict__ bf,
+                                 uint8_t* __restrict__ wimg, float* __restrict__ bview_fold, uint8_t* __restrict__ wimg_t) {
+  pack_fold_body(wv, wf, bv, bf, wimg, bview_fold, wimg_t);
+}
+
+__global__ void pack_fold_pair_kernel(const __grid_constant__ PackFoldPair f) {
+  const PackFoldNet& n = f.net[blockIdx.z];
+  pack_fold_body(n.wv, n.wf, n.bv, n.bf, n.wimg, n.bview_fold, n.wimg_t);
+}
+void launch_pack_fold_pair(const PackFoldPair& f, cudaStream_t st) {
+  pack_fold_pair_kernel<<<dim3(4, kViewHidden / 2, 2), 128, 0, st>>>(f);
 }
 
 // Device-side part of packing (no host synchronisation): swizzled bf16 K-block images, the transposed

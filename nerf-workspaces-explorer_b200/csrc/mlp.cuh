@@ -127,12 +127,22 @@ int dw_partial_rows();
 constexpr size_t kFoldScratchFloats = (size_t)kViewHidden * kHidden + kViewHidden;
 inline size_t mask_image_bytes(int64_t n_tiles) { return (size_t)(n_tiles + 1) * kMaskTileBytes; }
 const int* flat_offsets();
+size_t packed_transposed_bytes();
 int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st);
 int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st);
 constexpr int kMseMaxBlocks = 512;
 constexpr size_t kMseScratchBytes = (1 + 2 * kMseMaxBlocks) * sizeof(double);   // ticket word + per-block partial sums
 int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int64_t n_rays, float* d_c, float* d_f,
                     double* loss_scratch, double* loss_out, cudaStream_t st);
+// folded views layer of two networks in one launch (mlp.cu)
+struct PackFoldNet {
+  const float *wv, *wf, *bv, *bf;    // fp32 master: W_view [128][283], W_feature [256][256], b_view, b_feature
+  uint8_t* wimg; float* bview_fold; uint8_t* wimg_t;
+};
+struct PackFoldPair { PackFoldNet net[2]; };
+void launch_pack_fold_pair(const PackFoldPair& f, cudaStream_t st);
+int launch_adam_pack(PackedNet (&nets)[2], float* params, const float* grads, float* m, float* v, float lr, float b1,
+                     float b2, float eps, int step, float grad_scale, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 int step, float grad_scale, cudaStream_t st);
 

@@ -879,6 +879,82 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adam fused with the re-pack (both networks, ONE launch).  The optimiser step used to be 1 + 2 x 6 launches:
+// adam_kernel, then per network pack_weights / pack_dir / a D2D copy / pack_weights_t / fill_consts (+ pack_fold),
+// all tiny and latency-bound (0.25 ms of a 5 ms step).  Every derived image is a pure function of ONE parameter per
+// element, so the thread that updates a parameter also writes its bf16 copy into the forward K-block image and into
+// the transposed image of the dX kernel, or its fp32 copy into the device-side constants / view-direction table.
+// Only the folded views layer (a 256-long dot product per element) keeps its own kernel, one launch for both networks.
+// Same bytes as train_pack() of the updated parameters (tests/test_gpu_train.py compares the buffers).
+// ------------------------------------------------------------------------------------------------
+struct AdamPackNet {
+  float* params; const float* grads; float* m; float* v;     // flat [NWX_PARAMS_PER_NET], state_dict order
+  uint8_t* wimg; uint8_t* wimg_t; MlpConsts* gconsts; float* wdir_t; float* bview;
+};
+struct AdamPackArgs {
+  AdamPackNet net[2];
+  int off[NWX_NUM_WEIGHT_TENSORS + 1];
+  float step, inv_sqrt_bc2, bc2, b1, b2, eps, grad_scale;
+};
+
+__device__ __forceinline__ void put_bf16_swizzled(uint8_t* img, int n, int c, float v) {
+  reinterpret_cast<__nv_bfloat16*>(img)[n * 64 + ((((c >> 3) ^ (n & 7))) << 3) + (c & 7)] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256)
+adam_pack_kernel(const __grid_constant__ AdamPackArgs a) {
+  const int64_t total = 2 * (int64_t)NWX_PARAMS_PER_NET;
+  const float inv_sqrt_bc2 = rsqrtf(a.bc2);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int which = idx >= NWX_PARAMS_PER_NET ? 1 : 0;
+    const int i = (int)(idx - (int64_t)which * NWX_PARAMS_PER_NET);
+    const AdamPackNet& nt = a.net[which];
+    // torch.optim.Adam (same arithmetic as adam_kernel)
+    const float gi = nt.grads[i] * a.grad_scale;
+    const float mi = a.b1 * nt.m[i] + (1.f - a.b1) * gi;
+    const float vi = a.b2 * nt.v[i] + (1.f - a.b2) * gi * gi;
+    nt.m[i] = mi; nt.v[i] = vi;
+    const float p = nt.params[i] - a.step * mi / (sqrtf(vi) * inv_sqrt_bc2 + a.eps);
+    nt.params[i] = p;
+    // which tensor (24 sorted offsets: 5-step binary search)
+    int t = 0;
+#pragma unroll
+    for (int stp = 16; stp > 0; stp >>= 1)
+      if (t + stp < NWX_NUM_WEIGHT_TENSORS && i >= a.off[t + stp]) t += stp;
+    const int r = i - a.off[t];
+    if (t < 16) {
+      const int l = t >> 1;
+      if (t & 1) { nt.gconsts->bias[l][r] = p; continue; }                  // _pts_linears.l.bias
+      const int in_dim = l == 0 ? kPeXyz : (l == 5 ? kPeXyz + kHidden : kHidden);
+      const int o = r / in_dim, k = r - o * in_dim;                          // W[o][k]
+      // forward image: K-block kb, column c (layer 5 = [pe(63) | h(256)], nerf_model.py:59)
+      int kb, c;
+      if (l == 5 && k >= kPeXyz) { kb = 1 + ((k - kPeXyz) >> 6); c = (k - kPeXyz) & 63; }
+      else if (l == 0 || l == 5) { kb = 0; c = k; }
+      else { kb = k >> 6; c = k & 63; }
+      const int g = (l == 0 ? 0 : (l <= 5 ? 1 + 4 * (l - 1) : 22 + 4 * (l - 6))) + kb;
+      put_bf16_swizzled(nt.wimg + kblock_offset(g), o, c, p);
+      // transposed image of the dX kernel: step s = 8 - l, B[n = input feature][k = output feature]
+      if (l >= 1) {
+        const int c0 = l == 5 ? kPeXyz : 0;
+        if (k >= c0) {
+          const int s = 8 - l;
+          put_bf16_swizzled(nt.wimg_t + (size_t)(dx_step_kb0(s) + (o >> 6)) * kKBlockBytes, k - c0, o & 63, p);
+        }
+      }
+    } else if (t == 16) {                                                    // _views_linears.0.weight [128][283]
+      const int j = r / (kHidden + kPeDir), mcol = r - j * (kHidden + kPeDir);
+      if (mcol >= kHidden) nt.wdir_t[(mcol - kHidden) * kViewHidden + j] = p;  // [:, :256] goes through the fold
+    } else if (t == 17) nt.bview[r] = p;
+    else if (t == 19) nt.gconsts->bias[8][r] = p;                            // _feature_linear.bias (18: weight, fold only)
+    else if (t == 20) nt.gconsts->w_alpha[r] = p;
+    else if (t == 21) nt.gconsts->b_alpha = p;
+    else if (t == 22) (&nt.gconsts->w_rgb[0][0])[r] = p;
+    else if (t == 23) nt.gconsts->b_rgb[r] = p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 // offsets of the 24 tensors in the flat state_dict-ordered parameter / gradient buffer
@@ -895,6 +971,7 @@ struct FlatLayout {
 static const FlatLayout g_flat;
 
 const int* flat_offsets() { return g_flat.off; }
+size_t packed_transposed_bytes() { return (size_t)kDxKBlocks * kKBlockBytes; }
 
 // Re-pack one network from its flat fp32 master parameters (state_dict order): forward images,
 // transposed images for dX, device-side biases/heads.  Stream-ordered, no host synchronisation,
@@ -1067,6 +1144,39 @@ int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int
   if (blocks > kMseMaxBlocks) blocks = kMseMaxBlocks;
   mse_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(rgb_c, rgb_f, gt, n_rays * 3, d_c, d_f, loss_scratch + 1,
                                                     reinterpret_cast<unsigned int*>(loss_scratch), loss_out);
+  NWX_LAUNCHED();
+  return NWX_OK;
+}
+
+// Adam + re-pack of both networks: params / grads / m / v are [2][NWX_PARAMS_PER_NET] (coarse, then fine).
+int launch_adam_pack(PackedNet (&nets)[2], float* params, const float* grads, float* m, float* v, float lr, float b1,
+                     float b2, float eps, int step, float grad_scale, cudaStream_t st) {
+  AdamPackArgs a{};
+  for (int w = 0; w < 2; ++w) {
+    PackedNet& n = nets[w];
+    if (!n.wimg || !n.wimg_t || !n.gconsts || !n.wdir_t || !n.bview || !n.bview_fold) return NWX_E_NO_WEIGHTS;   // train_pack first
+    const size_t o = (size_t)w * NWX_PARAMS_PER_NET;
+    a.net[w] = AdamPackNet{params + o, grads + o, m + o, v + o, n.wimg, n.wimg_t, n.gconsts, n.wdir_t, n.bview};
+  }
+  for (int i = 0; i < NWX_NUM_WEIGHT_TENSORS; ++i) a.off[i] = g_flat.off[i];
+  a.off[NWX_NUM_WEIGHT_TENSORS] = NWX_PARAMS_PER_NET;
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  a.step = lr / bc1; a.inv_sqrt_bc2 = 0.0f /* filled on the device: rsqrtf(bc2) like adam_kernel */; a.bc2 = bc2; a.b1 = b1; a.b2 = b2; a.eps = eps; a.grad_scale = grad_scale;
+  int64_t blocks = (2 * (int64_t)NWX_PARAMS_PER_NET + 255) / 256;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  adam_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  NWX_LAUNCHED();
+  // folded views layer of both networks (reads the updated master parameters): one launch
+  PackFoldPair f{};
+  for (int w = 0; w < 2; ++w) {
+    const float* p = params + (size_t)w * NWX_PARAMS_PER_NET;
+    f.net[w] = PackFoldNet{p + g_flat.off[16], p + g_flat.off[18], p + g_flat.off[17], p + g_flat.off[19], nets[w].wimg,
+                           nets[w].bview_fold, nets[w].wimg_t};
+    nets[w].master = p;
+    nets[w].loaded = true;
+    nets[w].consts_stale = true;      // the host copy of the biases (inference launches) is now behind
+  }
+  launch_pack_fold_pair(f, st);
   NWX_LAUNCHED();
   return NWX_OK;
 }

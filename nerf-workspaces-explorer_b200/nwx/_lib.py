@@ -63,6 +63,8 @@ PROTOTYPES = {
     "nwx_train_pack": (_i, [_vp, _i, _vp, _vp]),
     "nwx_train_fwd_bwd": (_i, [_vp, C.POINTER(TrainIO), _i64, C.POINTER(RenderOpts), _vp]),
     "nwx_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp]),
+    "nwx_adam_pack_step": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp]),
+    "nwx_debug_copy_packed": (_i, [_vp, _i, _i, _vp, _i64, _vp]),
     "nwx_ctx_set_profiling": (_i, [_vp, _i]),
     "nwx_ctx_stage_ms": (_i, [_vp, C.POINTER(_f)]),
     "nwx_render_rays": (_i, [_vp, _vp, _i64, C.POINTER(RenderOpts), C.POINTER(RenderOut), _vp]),

@@ -115,6 +115,19 @@ class Trainer:
             check(self.engine._lib.nwx_train_pack(self.engine._ctx, w, self.params[w].data_ptr(), _stream()),
                   "nwx_train_pack")
 
+    PACKED = {"wimg": (0, 1245184), "wimg_t": (1, 983040), "consts": (2, None), "wdir_t": (3, 27 * 128 * 4),
+              "bview": (4, 512), "bview_fold": (5, 512)}
+
+    def packed_bytes(self, which: int, what: str) -> torch.Tensor:
+        """Test hook: one packed device buffer of a network as a uint8 tensor (see nwx_debug_copy_packed)."""
+        code, size = self.PACKED[what]
+        if size is None:
+            size = 4 * (9 * 256 + 256 + 3 * 128 + 4)            # sizeof(MlpConsts)
+        out = torch.empty((size,), device=self.device, dtype=torch.uint8)
+        check(self.engine._lib.nwx_debug_copy_packed(self.engine._ctx, which, code, out.data_ptr(), size, _stream()),
+              "nwx_debug_copy_packed")
+        return out
+
     def sync_inference_weights(self) -> None:
         """Refresh the engine's inference-side copy (host constants) from the master parameters."""
         self.pack()                                              # training-side images / device constants
@@ -226,13 +239,12 @@ class Trainer:
 
     def apply_optimizer(self, global_step: int, grad_scale: float = 1.0) -> None:
         """Adam on self.grads * grad_scale, re-pack, learning-rate schedule (the local part of optimizer_step)."""
-        scale = grad_scale
         self.opt_steps += 1
-        n = self.params.numel()
-        check(self.engine._lib.nwx_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
-                                             self.v.data_ptr(), n, self.lr, self.betas[0], self.betas[1], self.eps,
-                                             self.opt_steps, scale, _stream()), "nwx_adam_step")
-        self.pack()
+        # two launches: Adam over both networks fused with the re-pack of every kernel image, then the folded views layer
+        check(self.engine._lib.nwx_adam_pack_step(self.engine._ctx, self.params.data_ptr(), self.grads.data_ptr(),
+                                                  self.m.data_ptr(), self.v.data_ptr(), self.lr, self.betas[0],
+                                                  self.betas[1], self.eps, self.opt_steps, grad_scale, _stream()),
+              "nwx_adam_pack_step")
         self.lr = self.lr0 * (self.lr_decay_rate ** (global_step / self.lr_decay_steps))
 
     def step(self, rays: torch.Tensor, gt_rgb: torch.Tensor, global_step: int, **rand) -> torch.Tensor:

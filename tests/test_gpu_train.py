@@ -262,3 +262,35 @@ def test_in_kernel_rng_statistics_and_equivalence():
     l2 = tr.forward_backward(rays, gt, t_rand, u, nc, nf).clone(); g2 = tr.grads.clone()
     assert torch.equal(l1, l2)
     assert float((g1 - g2).abs().max()) <= 1e-6 * float(g2.abs().max())
+
+
+def test_fused_adam_pack_writes_the_same_images_as_train_pack():
+    """The optimiser step is two launches (Adam fused with the re-pack of every kernel image, then the folded views
+    layer).  After a few steps every packed buffer must equal, byte for byte, what nwx_train_pack produces from the
+    same master parameters; and the fused Adam must agree with the stand-alone Adam kernel."""
+    import nwx
+    from nwx._lib import check
+    g = load_golden("render_train")
+    rays, gt = g["rays"].to(DEV), g["gt"].float().to(DEV)
+    tr = nwx.Trainer(nwx.Engine(torch.device(DEV)), *_nets(), lr=1e-2, seed=3)        # big steps: every weight moves
+    p0, m0, v0 = tr.params.clone(), tr.m.clone(), tr.v.clone()
+    tr.forward_backward(rays, gt)
+    grads = tr.grads.clone()
+    tr.apply_optimizer(0)
+    # (a) same update as nwx_adam_step
+    check(nwx.lib().nwx_adam_step(p0.data_ptr(), grads.data_ptr(), m0.data_ptr(), v0.data_ptr(), p0.numel(), 1e-2, 0.9, 0.999,
+                                  1e-8, 1, 1.0, torch.cuda.current_stream().cuda_stream))
+    assert float((tr.params - p0).abs().max()) <= 1e-7 and float((tr.m - m0).abs().max()) <= 1e-9
+    for s in range(1, 3):
+        tr.step(rays, gt, s)
+    names = ("wimg", "wimg_t", "consts", "wdir_t", "bview", "bview_fold")
+    fused = {(w, n): tr.packed_bytes(w, n).clone() for w in (0, 1) for n in names}
+    tr.pack()                                                        # the reference: six pack kernels per network
+    for (w, n), buf in fused.items():
+        ref = tr.packed_bytes(w, n)
+        if n == "wimg":                                              # the unfolded feature / views images are not
+            cut = 30 * 32768                                         # maintained during training (K-blocks 30..37)
+            fold0 = 34 * 32768 + 4 * 16384
+            assert torch.equal(buf[:cut], ref[:cut]) and torch.equal(buf[fold0:], ref[fold0:]), (w, n)
+        else:
+            assert torch.equal(buf, ref), (w, n)
