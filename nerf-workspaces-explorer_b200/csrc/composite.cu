@@ -48,7 +48,12 @@ __device__ __forceinline__ float sigmoidf_rn(float x) {        // torch.sigmoid:
 // expf + reciprocal (~35 instructions, three per sample: they made the forward instruction-bound).  Colours
 // carry the 1e-3 tolerance of the bf16 MLP; the weights (alpha, transmittance), which decide the
 // importance-sampling indices, keep the exact op-for-op arithmetic.  The backward keeps sigmoidf_rn.
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_fast(float x) {      // FMUL, MUFU.EX2, FADD, MUFU.RCP
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // numpy (255 * clip(x, 0, 1)).astype(uint8): fp32 multiply, truncation; NaN -> 0  (model_utils.py:9)
 __device__ __forceinline__ uint8_t to8b_one(float v) {
@@ -127,13 +132,12 @@ __device__ __forceinline__ float ray_dnorm(const float* __restrict__ rays_d, int
 //   * direct: per-lane __ldg of the same runs (any alignment, any S); also the A/B baseline (NWX_COMPOSITE=direct).
 template <int K>
 __device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float (&zr)[K + 1], const float (&nz)[K], bool noisy,
-                                              int64_t ray, int S, int lane, const float* __restrict__ rays_d, int d_stride,
+                                              int64_t ray, int S, int lane, float dnorm,
                                               int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
                                               float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
                                               uint8_t* __restrict__ rgb8, int& bad) {
   const int s0 = lane * K;
   const int64_t base = ray * S;
-  const float dnorm = ray_dnorm(rays_d, d_stride, ray);
   float alpha[K];
   double tloc[K];                                             // product of t over my samples before j
   double p = 1.0;
@@ -184,11 +188,15 @@ __device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float
     if (disp) disp[ray] = dspv;
     if (acc) acc[ray] = a_w;
     if (depth) depth[ray] = a_d;
-    const float chk[6] = {a_r, a_g, a_b, dspv, a_w, a_d};
+    // NaN / Inf screening (inference handler:273-275): the sum of the magnitudes is finite iff every value is
+    const float mag = fabsf(a_r) + fabsf(a_g) + fabsf(a_b) + fabsf(dspv) + fabsf(a_w) + fabsf(a_d);
+    if (!(mag < INFINITY)) {
+      const float chk[6] = {a_r, a_g, a_b, dspv, a_w, a_d};
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      if (chk[c] != chk[c]) bad |= 1;
-      else if (fabsf(chk[c]) == INFINITY) bad |= 2;
+      for (int c = 0; c < 6; ++c) {
+        if (chk[c] != chk[c]) bad |= 1;
+        else if (fabsf(chk[c]) == INFINITY) bad |= 2;
+      }
     }
   }
 }
@@ -219,7 +227,8 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       nz[j] = noise ? __ldg(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
     }
     zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // z of the sample after my last one
-    composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, rays_d, d_stride, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad);
+    composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, ray_dnorm(rays_d, d_stride, ray), white_bkgd, rgb, disp, acc, depth,
+                     weights, rgb8, bad);
   }
   if (flags && bad) atomicOr(flags, bad);
 }
@@ -266,6 +275,7 @@ composite_fwd_bulk_kernel(const float* __restrict__ raw, const float* __restrict
       const int64_t idx = base + (s < S ? s : S - 1);
       nz[j] = noise ? __ldg(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
     }
+    const float dnorm = ray_dnorm(rays_d, d_stride, ray);       // issued before the wait: its latency hides behind it
     mbar_wait(bar, phase, wc);
     phase ^= 1u;
 #pragma unroll
@@ -277,7 +287,7 @@ composite_fwd_bulk_kernel(const float* __restrict__ raw, const float* __restrict
     zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // z of the sample after my last one
     __syncwarp();                                               // every lane has its registers: the buffer is free
     if (lane == 0 && ray + nwarps < N) fetch(ray + nwarps);     // next ray's bytes fly underneath this ray's math
-    composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, rays_d, d_stride, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad);
+    composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, dnorm, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad);
   }
   if (flags && bad) atomicOr(flags, bad);
 }

@@ -103,6 +103,52 @@ struct DxArgs {
 
 enum { kBwdLinear = 0, kBwdSigmaMask = 1, kBwdMask = 2 };
 
+// ReLU' of packed word p of a 32-column chunk as an AND mask for the packed bf16 pair: bit p of the forward's mask
+// word -> 0x0000FFFF, bit 16 + p -> 0xFFFF0000.  One shift puts the two bits on the sign positions of bytes 0 and 2,
+// one PRMT in sign-replicate mode (selector nibble | 8) smears them over the two halves: 2 instructions per PAIR of
+// elements instead of a test + select per element (the per-element form was 28 % of the kernel's instructions and
+// made the epilogue warps issue-bound).
+template <int kP>
+__device__ __forceinline__ uint32_t relu_pair_mask(uint32_t m) {
+  const uint32_t x = kP <= 7 ? (m << (7 - kP)) : (m >> (kP - 7));
+  uint32_t sel;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sel) : "r"(x), "r"(0u), "r"(0xAA88u));
+  return sel;
+}
+
+template <int kKind, int kJ>
+__device__ __forceinline__ void bwd_pack_pairs(const MlpConsts& cst, const uint32_t (&v)[32], int col, uint32_t m, float dsig,
+                                               uint32_t (&pk)[16]) {
+  if constexpr (kJ < 16) {
+    float a = __uint_as_float(v[2 * kJ]), b = __uint_as_float(v[2 * kJ + 1]);
+    if (kKind == kBwdSigmaMask) {                   // d h8 += dsigma * w_alpha (sigma head, nerf_model.py:63)
+      a = fmaf(dsig, cst.w_alpha[col + 2 * kJ], a);
+      b = fmaf(dsig, cst.w_alpha[col + 2 * kJ + 1], b);
+    }
+    uint32_t w = pack_bf16x2(a, b);
+    if (kKind != kBwdLinear) w &= relu_pair_mask<kJ>(m);     // ReLU': the saved activation is > 0
+    pk[kJ] = w;
+    bwd_pack_pairs<kKind, kJ + 1>(cst, v, col, m, dsig, pk);
+  }
+}
+
+template <int kKind>
+__device__ __forceinline__ void bwd_chunk(const MlpConsts& cst, const uint32_t (&v)[32], int col, uint32_t m, float dsig,
+                                          uint32_t hrow, bool to_smem, bool to_gmem, int row, uint8_t* grow) {
+  uint32_t pk[16];
+  bwd_pack_pairs<kKind, 0>(cst, v, col, m, dsig, pk);
+  const uint32_t kbo = (uint32_t)(col >> 6) * kTileImgBytes;
+  const int j0 = (col & 63) >> 3, r7 = row & 7;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t off = kbo + (((j0 + q) ^ r7) << 4);
+    if (to_smem) st_shared_v4(hrow + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    if (to_gmem) *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
+// One thread = one row (point) over its 128-column half, in four 32-column chunks; the TMEM load of chunk c + 1 is
+// in flight while chunk c is processed (like the forward's epilogue_hidden).
 template <int kKind>
 __device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tmem, uint32_t hrow, bool to_smem, bool to_gmem,
                                              int row, int wg, const uint32_t* mrow, uint8_t* grow, float dsig) {
@@ -111,36 +157,20 @@ __device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tm
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) mask[cc] = __ldg(mrow + (wg * 4 + cc) * kTileM);
   }
-#pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
-    const int col = wg * 128 + cc * 32;
-    const uint32_t kbo = (uint32_t)(col >> 6) * kTileImgBytes;
-    const int j0 = (col & 63) >> 3;
-    const uint32_t m = mask[cc];
-    uint32_t v[32];
-    tmem_ld32(d_tmem + col, v);
-    tmem_wait_ld();
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-      if (kKind == kBwdSigmaMask) {                 // d h8 += dsigma * w_alpha (sigma head, nerf_model.py:63)
-        a = fmaf(dsig, cst.w_alpha[col + j], a);
-        b = fmaf(dsig, cst.w_alpha[col + j + 1], b);
-      }
-      if (kKind != kBwdLinear) {                    // ReLU': the saved activation is > 0
-        a = (m & (1u << (j >> 1))) ? a : 0.0f;
-        b = (m & (0x10000u << (j >> 1))) ? b : 0.0f;
-      }
-      pk[j >> 1] = pack_bf16x2(a, b);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t off = kbo + (((j0 + q) ^ (row & 7)) << 4);
-      if (to_smem) st_shared_v4(hrow + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      if (to_gmem) *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    }
-  }
+  const int col0 = wg * 128;
+  uint32_t va[32], vb[32];
+  tmem_ld32(d_tmem + col0, va);
+  tmem_wait_ld_dep(va);
+  tmem_ld32(d_tmem + col0 + 32, vb);
+  bwd_chunk<kKind>(cst, va, col0, mask[0], dsig, hrow, to_smem, to_gmem, row, grow);
+  tmem_wait_ld_dep(vb);
+  tmem_ld32(d_tmem + col0 + 64, va);
+  bwd_chunk<kKind>(cst, vb, col0 + 32, mask[1], dsig, hrow, to_smem, to_gmem, row, grow);
+  tmem_wait_ld_dep(va);
+  tmem_ld32(d_tmem + col0 + 96, vb);
+  bwd_chunk<kKind>(cst, va, col0 + 64, mask[2], dsig, hrow, to_smem, to_gmem, row, grow);
+  tmem_wait_ld_dep(vb);
+  bwd_chunk<kKind>(cst, vb, col0 + 96, mask[3], dsig, hrow, to_smem, to_gmem, row, grow);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)

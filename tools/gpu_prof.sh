@@ -14,7 +14,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 echo "ncu list rc=$?"
 timeout 300 python tools/train_bench.py --steps 4 > $OUT/train_plain.log 2>&1
 echo "train rc=$?"; tail -1 $OUT/train_plain.log | cut -c1-400
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -k regex:nwx -s 300 -c 260 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 250 -c 150 --csv \
     --log-file $OUT/train_launches_warm.csv python tools/train_bench.py --steps 4 > $OUT/ncu_train.log 2>&1
 echo "ncu train list rc=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on \

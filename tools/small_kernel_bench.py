@@ -62,6 +62,17 @@ def worker(iters: int) -> dict:
     for k, v in res.items():
         b = BYTES_PER_RAY.get(k.replace("_with_inds", ""), 0) + (1024 if k.endswith("inds") else 0)
         v["algorithmic_gbs"] = b * N / (v["ms"] * 1e-3) / 1e9
+    # what this box's HBM does for the three access mixes (torch library kernels, 4 GiB each): the training
+    # forward / dX kernels are write-dominated, dW is read-only, the peak in MEASURED_PEAKS.json is a copy
+    del out, raw_c, raw_f
+    a = torch.empty(1 << 30, device=dev, dtype=torch.float32)
+    b = torch.empty(1 << 30, device=dev, dtype=torch.float32)
+    ms, _ = timeit(lambda: a.zero_())
+    res["hbm_write_only_gbs"] = a.numel() * 4 / (ms * 1e-3) / 1e9
+    ms, _ = timeit(lambda: torch.sum(a))
+    res["hbm_read_only_gbs"] = a.numel() * 4 / (ms * 1e-3) / 1e9
+    ms, _ = timeit(lambda: b.copy_(a))
+    res["hbm_copy_gbs"] = 2 * a.numel() * 4 / (ms * 1e-3) / 1e9
     return res
 
 
@@ -81,7 +92,8 @@ def main():
         lines = [l for l in proc.stdout.splitlines() if l.startswith("RESULT ")]
         out[name] = json.loads(lines[-1][7:]) if lines else {"error": proc.stderr[-800:]}
     if all("error" not in v for v in out.values()):
-        out["bit_identical"] = {k: out["production"][k]["crc"] == out["fallbacks"][k]["crc"] for k in out["production"]}
+        out["bit_identical"] = {k: out["production"][k]["crc"] == out["fallbacks"][k]["crc"]
+                                for k, v in out["production"].items() if isinstance(v, dict)}
     print(json.dumps(out))
 
 
