@@ -26,6 +26,7 @@ struct nwx_ctx {
   int64_t scratch_generation = 0;   // bumped whenever the scratch is re-allocated (captured CUDA graphs hold its address)
   float* dbg_out = nullptr;      // optional tap target set by nwx_debug_tap
   int dbg_layer = -1;
+  int experiment = 0;            // timing experiments in the training kernels (results wrong on purpose), 0 = none
   uint32_t* diag = nullptr;      // host-mapped diagnostics the kernels write before aborting (own_diag unless overridden)
   uint32_t* own_diag = nullptr;  // 4 words of mapped pinned host memory, allocated with the context
   // optional per-stage device timing of nwx_render_rays (bench.py: roofline of the dominant kernel)
@@ -172,6 +173,13 @@ extern "C" int nwx_debug_tap(nwx_ctx* ctx, int layer, float* out) {
 extern "C" int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped) {
   NWX_REQUIRE(ctx);
   ctx->diag = host_mapped ? host_mapped : ctx->own_diag;
+  return NWX_OK;
+}
+// Timing experiments in the training forward / dX kernels (tools/train_experiments.py); results are WRONG on purpose:
+// 11 = the epilogues do not wait for the previous TMA store of their tile, 12 = no TMA stores of the tile images at all.
+extern "C" int nwx_debug_experiment(nwx_ctx* ctx, int code) {
+  NWX_REQUIRE(ctx && (code == 0 || code == 11 || code == 12));
+  ctx->experiment = code;
   return NWX_OK;
 }
 extern "C" int nwx_ctx_last_diag(nwx_ctx* ctx, uint32_t* out4) {
@@ -476,6 +484,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     a.which = which;
     a.rays = io->rays; a.z = z; a.wimg = net.wimg; a.dirbias = dirb; a.raw_out = raw; a.diag = ctx->diag;
     a.acts = acts[which]; a.masks = masks[which]; a.hv_out = hv[which]; a.P = N * S; a.ray_dim = rd; a.S = S;
+    a.experiment = ctx->experiment;
     return nwx::launch_mlp_train_forward(net, a, st);
   };
   const nwx::RngSpec rj = rng_for(o, 0, o->t_rand, o->rng_jitter != 0), ru = rng_for(o, 1, o->u, o->rng_u != 0);
@@ -507,6 +516,7 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     b.fold_scratch = reinterpret_cast<float*>(ts + tp.fold);
     b.pe_dir = pe_dir; b.grad = grads[w]; b.diag = ctx->diag; b.P = N * S[w]; b.S = S[w]; b.max_partials = ctx->n_partials;
     b.which = w;
+    b.experiment = ctx->experiment;
     if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st))) return rc;
     // data-parallel callers all-reduce the coarse network's gradients underneath the fine network's backward
     if (w == 0 && io->ev_coarse_done) NWX_CUDA_TRY(cudaEventRecord((cudaEvent_t)io->ev_coarse_done, st));

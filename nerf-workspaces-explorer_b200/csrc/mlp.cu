@@ -426,7 +426,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (kTrain) {
             // the TMA store that saved this buffer's previous contents must have finished reading it
             // (groups complete in order: all but the newest one, which belongs to the other tile)
-            if (warp == 8 && lane == 0) bulk_wait_read<1>();
+            if (warp == 8 && lane == 0 && args.experiment == 0) bulk_wait_read<1>();
             named_bar_sync(3, 256);
           }
           float* tap_row = nullptr;
@@ -519,7 +519,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             // training: the activation tile just written IS the image the backward wants -- one TMA
             // store of the whole 64 KB tile instead of 16 global stores per thread
             named_bar_sync(3, 256);              // every warp's tile writes are fenced
-            if (warp == 8 && lane == 0 && args.acts != nullptr && tile_of(it, t) < args.n_tiles)
+            if (warp == 8 && lane == 0 && args.acts != nullptr && tile_of(it, t) < args.n_tiles && args.experiment != 12)
               bulk_s2g(args.acts + tile_img_offset(act_slot_kb0(l + 1), 4, args.n_tiles, tile_of(it, t), 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
           }

@@ -91,6 +91,7 @@ struct MlpArgs {
   int64_t P;                         // total points
   int64_t n_tiles;                   // ceil(P / 128)
   int ray_dim, S, iters, dbg_layer, which;
+  int experiment;                    // training forward timing experiments (nwx_debug_experiment), 0 = none
 };
 
 int pack_network(PackedNet& net, const float* const* tensors, cudaStream_t st);
@@ -117,6 +118,7 @@ struct TrainBwdArgs {
   uint32_t* diag;
   int64_t P;
   int S, max_partials, which;
+  int experiment;            // dX timing experiments (nwx_debug_experiment), 0 = none
 };
 int upload_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);       // backward kernels (train.cu)
 int upload_fwd_train_consts(int which, const MlpConsts* dev_src, cudaStream_t st);   // training forward (mlp.cu)

@@ -98,7 +98,7 @@ struct DxArgs {
   const MlpConsts* gconsts;
   uint32_t* diag;
   int64_t P, n_tiles;
-  int iters, which;
+  int iters, which, experiment;
 };
 
 enum { kBwdLinear = 0, kBwdSigmaMask = 1, kBwdMask = 2 };
@@ -361,7 +361,7 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           // TMA store; the last two store per thread: after the last MMA the G_views producers reuse the
           // buffer, and they cannot wait on another thread's bulk group.
           const bool via_tma = s < kDxSteps - 2;
-          if (warp == 8 && lane == 0) bulk_wait_read<1>();      // earlier store of this buffer has finished reading it
+          if (warp == 8 && lane == 0 && args.experiment == 0) bulk_wait_read<1>();   // earlier store of this buffer has finished reading it
           named_bar_sync(3, 256);
           if (s == 0) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, dsig[t]);
           else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, !via_tma, row, wg, mrow, grow, 0.f);
@@ -371,7 +371,7 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           if (lane == 0) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
           if (via_tma) {
             named_bar_sync(3, 256);                             // every warp's tile writes are fenced
-            if (warp == 8 && lane == 0)
+            if (warp == 8 && lane == 0 && args.experiment != 12)
               bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 2), 4, args.n_tiles + 1, wt, 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
           }
@@ -1063,7 +1063,7 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     }
     DxArgs d{};
     d.d_raw = a.d_raw; d.hv = a.hv; d.acts = a.acts; d.masks = a.masks; d.grads = a.gimg; d.wimg_t = net.wimg_t; d.gconsts = net.gconsts;
-    d.diag = a.diag; d.P = a.P; d.n_tiles = tiles; d.which = a.which;
+    d.diag = a.diag; d.P = a.P; d.n_tiles = tiles; d.which = a.which; d.experiment = a.experiment;
     const int units = (num_sms() & ~1) / 2;
     int64_t need = (tiles + 3) / 4;
     const int use = (int)(need < units ? need : units);

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "nwx_set_mlp_variant": (_i, [_vp, _i]),
     "nwx_debug_tap": (_i, [_vp, _i, _vp]),
     "nwx_debug_diag": (_i, [_vp, _vp]),
+    "nwx_debug_experiment": (_i, [_vp, _i]),
     "nwx_ctx_last_diag": (_i, [_vp, C.POINTER(C.c_uint32)]),
     "nwx_sample_training_batch": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
 }
