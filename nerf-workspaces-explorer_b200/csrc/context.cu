@@ -176,9 +176,11 @@ extern "C" int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped) {
   return NWX_OK;
 }
 // Timing experiments in the training forward / dX kernels (tools/train_experiments.py); results are WRONG on purpose:
-// 11 = the epilogues do not wait for the previous TMA store of their tile, 12 = no TMA stores of the tile images at all.
+// 11 = the epilogues do not wait for the previous TMA store of their tile, 12 = no TMA stores of the tile images at all,
+// 13 = the forward neither builds nor stores the ReLU' bit masks, 14 = no named barriers around the tile writes (and 11),
+// 15 = the forward does not store the views hidden.
 extern "C" int nwx_debug_experiment(nwx_ctx* ctx, int code) {
-  NWX_REQUIRE(ctx && (code == 0 || code == 11 || code == 12));
+  NWX_REQUIRE(ctx && (code == 0 || (code >= 11 && code <= 15)));
   ctx->experiment = code;
   return NWX_OK;
 }

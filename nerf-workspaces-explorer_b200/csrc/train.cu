@@ -151,12 +151,8 @@ __device__ __forceinline__ void bwd_chunk(const MlpConsts& cst, const uint32_t (
 // in flight while chunk c is processed (like the forward's epilogue_hidden).
 template <int kKind>
 __device__ __forceinline__ void bwd_epilogue(const MlpConsts& cst, uint32_t d_tmem, uint32_t hrow, bool to_smem, bool to_gmem,
-                                             int row, int wg, const uint32_t* mrow, uint8_t* grow, float dsig) {
-  uint32_t mask[4] = {0u, 0u, 0u, 0u};                // ReLU' of this row's four 32-column chunks (forward's bit words)
-  if (kKind != kBwdLinear) {
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) mask[cc] = __ldg(mrow + (wg * 4 + cc) * kTileM);
-  }
+                                             int row, int wg, const uint32_t (&mask)[4] /* ReLU' bit words of this row's four
+                                             32-column chunks, loaded one step ahead */, uint8_t* grow, float dsig) {
   const int col0 = wg * 128;
   uint32_t va[32], vb[32];
   tmem_ld32(d_tmem + col0, va);
@@ -290,11 +286,14 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
             for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + q * 32));
           }
         }
-        if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
         const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
         uint8_t* grow = (tile < args.n_tiles)
                             ? args.grads + tile_img_offset(grad_slot_kb0(0), 2, args.n_tiles + 1, tile, 0) + row * 128 : nullptr;
-#pragma unroll 2
+        // The whole row (128 columns = 64 packed words) is computed and saved to HBM BEFORE the wait for the
+        // shared-memory tile: the hv loads (L2 latency, 32 per thread) then overlap the previous iteration's last
+        // MMAs instead of sitting between them and this tile's first one; after the wait only 16 STS.128 remain.
+        uint32_t pk[64];
+#pragma unroll
         for (int c8 = 0; c8 < 16; ++c8) {                       // 16 chunks of 8 columns = 128 columns
           float hvv[8];
           if (live) {
@@ -306,7 +305,6 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) hvv[e] = 0.f;
           }
-          uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             float g[2];
@@ -316,11 +314,18 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
               const float v = fmaf(cst.w_rgb[0][j], dr.x, fmaf(cst.w_rgb[1][j], dr.y, cst.w_rgb[2][j] * dr.z));
               g[h] = hvv[e + h] > 0.f ? v : 0.f;
             }
-            pk[e >> 1] = pack_bf16x2(g[0], g[1]);
+            pk[c8 * 4 + (e >> 1)] = pack_bf16x2(g[0], g[1]);
           }
+          if (grow) {
+            const uint32_t off = (uint32_t)(c8 >> 3) * kTileImgBytes + (((c8 & 7) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+          }
+        }
+        if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
+#pragma unroll
+        for (int c8 = 0; c8 < 16; ++c8) {
           const uint32_t off = (uint32_t)(c8 >> 3) * kTileImgBytes + (((c8 & 7) ^ (row & 7)) << 4);
-          st_shared_v4(hrow + off, pk[0], pk[1], pk[2], pk[3]);
-          if (grow) *reinterpret_cast<uint4*>(grow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(hrow + off, pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -333,6 +338,19 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
     const int quad = warp & 3, wg = (warp - 8) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    // ReLU' bit words (forward's masks) of the row's four 32-column chunks, per in-flight tile; always loaded ONE STEP
+    // AHEAD (right after the previous step's epilogue of the same tile), so the L2 latency of these four loads is
+    // covered by an MMA step instead of opening every epilogue
+    uint32_t mreg[2][4];
+    auto load_masks = [&](int64_t tile, int layer, uint32_t (&m)[4]) {
+      const int64_t mt = tile < args.n_tiles ? tile : 0;
+      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(
+                                 reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(mt, layer)) + row;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) m[cc] = __ldg(mrow + (wg * 4 + cc) * kTileM);
+    };
+#pragma unroll
+    for (int t = 0; t < 2; ++t) load_masks(tile_of(0, t), 7, mreg[t]);
     for (int it = 0; it < iters; ++it) {
       float dsig[2];
 #pragma unroll
@@ -353,35 +371,27 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           const uint32_t hrow = sbase + L::h0 + t * kHBytes + row * 128;
           // step s produces G_{8-s} = dL/d(pre-activation of pts layer 7-s) -> grad slot s + 2 (slot 1 is unused)
           uint8_t* grow = args.grads + tile_img_offset(grad_slot_kb0(s + 2), 4, args.n_tiles + 1, wt, 0) + row * 128;
-          // mask = ReLU' of the activation the produced gradient flows into: step 0 -> h8 (pts layer 7) ... step 7 -> h1
-          const int64_t mt = tile < args.n_tiles ? tile : 0;
-          const uint32_t* mrow = reinterpret_cast<const uint32_t*>(
-                                     reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(mt, 7 - s)) + row;
+          // mreg[t] = ReLU' of the activation the produced gradient flows into: step 0 -> h8 (pts layer 7) ... step 7 -> h1
           // All but the last two steps leave their G tile in smem (next step's A operand) and save it with ONE
           // TMA store; the last two store per thread: after the last MMA the G_views producers reuse the
           // buffer, and they cannot wait on another thread's bulk group.
           const bool via_tma = s < kDxSteps - 2;
           if (warp == 8 && lane == 0 && args.experiment == 0) bulk_wait_read<1>();   // earlier store of this buffer has finished reading it
-          named_bar_sync(3, 256);
-          if (s == 0) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mrow, grow, dsig[t]);
-          else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, !via_tma, row, wg, mrow, grow, 0.f);
+          if (args.experiment != 14) named_bar_sync(3, 256);
+          if (s == 0) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mreg[t], grow, dsig[t]);
+          else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, !via_tma, row, wg, mreg[t], grow, 0.f);
+          // next use of this tile slot: step s + 1 of the same tile, or step 0 of the next iteration's tile
+          if (s + 1 < kDxSteps) load_masks(tile, 6 - s, mreg[t]);
+          else if (it + 1 < iters) load_masks(tile_of(it + 1, t), 7, mreg[t]);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
           if (via_tma) {
-            named_bar_sync(3, 256);                             // every warp's tile writes are fenced
+            if (args.experiment != 14) named_bar_sync(3, 256);                             // every warp's tile writes are fenced
             if (warp == 8 && lane == 0 && args.experiment != 12)
               bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 2), 4, args.n_tiles + 1, wt, 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
-          }
-          // the next step's ReLU' bit words (four 128 B lines per warp): pull them into L2 now, one MMA
-          // step ahead, so the epilogue's loads do not wait on DRAM
-          if (s + 1 < kDxSteps && tile < args.n_tiles && lane == 0) {
-            const uint8_t* nm = reinterpret_cast<const uint8_t*>(args.masks) + mask_img_offset(tile, 6 - s) +
-                                (size_t)(wg * 4) * 512 + quad * 128;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + cc * 512));
           }
         }
       }

@@ -4,6 +4,9 @@ kernels' timing experiments switched on (nwx_debug_experiment; gradients are WRO
    0  production
   11  forward / dX epilogues do not wait for the previous TMA store of their shared-memory tile
   12  no TMA stores of the activation / gradient tile images at all
+  13  the forward neither builds nor stores the ReLU' bit masks
+  14  no named barriers around the tile writes (the store's wait is skipped too)
+  15  the forward does not store the views hidden
 Prints one JSON line with ms per step and the per-kernel CUDA-event times of forward, dX and the rest."""
 import json
 import os
@@ -30,7 +33,7 @@ def main():
     rays = bank[torch.randint(0, bank.shape[0], (4096,), device=dev, generator=gen)]
     gt = torch.rand((4096, 3), device=dev, generator=gen)
     out = {}
-    for code in (0, 11, 12, 0):
+    for code in (0, 11, 12, 13, 14, 15, 0):
         check(nwx.lib().nwx_debug_experiment(eng._ctx, code))
         for i in range(3):
             tr.forward_backward(rays, gt)
