@@ -285,8 +285,11 @@ composite_fwd_bulk_kernel(const float* __restrict__ raw, const float* __restrict
       zr[j] = s_z[wib][sc];
     }
     zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // z of the sample after my last one
-    __syncwarp();                                               // every lane has its registers: the buffer is free
-    if (lane == 0 && ray + nwarps < N) fetch(ray + nwarps);     // next ray's bytes fly underneath this ray's math
+    __syncwarp();                                               // every lane's reads of the buffer are ordered before ...
+    if (lane == 0 && ray + nwarps < N) {
+      fence_proxy_async_smem();                                 // ... the async proxy's writes into it (generic -> async)
+      fetch(ray + nwarps);                                      // next ray's bytes fly underneath this ray's math
+    }
     composite_ray<K>(rw, zr, nz, noisy, ray, S, lane, dnorm, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad);
   }
   if (flags && bad) atomicOr(flags, bad);
