@@ -41,13 +41,16 @@ def worker(iters: int) -> dict:
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
+        times = []                      # median of per-launch times: the wrappers allocate their outputs (hundreds of
+        for _ in range(iters):          # MB), and an occasional cudaMalloc inside the loop would spoil a mean
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             r = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters, r
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        times.sort()
+        return times[len(times) // 2], r
 
     crc = lambda *ts: zlib.crc32(b"".join(t.detach().cpu().numpy().tobytes() for t in ts if t is not None))
     res = {}
