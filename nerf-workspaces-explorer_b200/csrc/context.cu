@@ -158,7 +158,7 @@ extern "C" int nwx_load_weights(nwx_ctx* ctx, int which, const float* const* ten
 }
 
 extern "C" int nwx_set_mlp_variant(nwx_ctx* ctx, int variant) {
-  NWX_REQUIRE(ctx && variant >= 0 && variant <= 4);
+  NWX_REQUIRE(ctx && variant >= 0 && variant <= 5);
   ctx->mlp_variant = variant;
   return NWX_OK;
 }
