@@ -192,14 +192,14 @@ __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, ui
   return f32x2_lo(sig) + f32x2_hi(sig);
 }
 
-// kPe1 (production since round 2): ONE positional-encoding buffer instead of one per in-flight tile, a FIFTH weight
-// slot in the 16 KB this frees.  Layer 0 reads a tile's encoding from the first K-block of the tile's own activation
-// buffer (empty at that point: the layer-0 epilogue overwrites it with h1 after the MMA has consumed it); the skip layer
-// (l = 5) reads it from the shared buffer, which the PE warps refill from the packed features they keep in registers
-// -- tile 0's, then, as soon as the tensor core has consumed those (pe5_free), tile 1's.  So that the refill hides,
-// the skip layer is issued tile-major (tile 0: encoding block + 4 hidden blocks, then tile 1) with all 5 of its weight
-// K-blocks resident.  With 5 slots a 4-block layer leaves one slot free, so the next layer's first K-block is prefetched
-// a whole tile earlier: the ~260-cycle wait of every layer's first MMA on the 4-slot ring goes away.
+// kPe1: ONE positional-encoding buffer instead of one per in-flight tile, a FIFTH weight slot in the 16 KB this frees.
+// The buffer is filled four times per iteration from the packed features the PE warps keep in registers -- tile 0 /
+// tile 1 for layer 0, tile 0 / tile 1 for the skip layer (l = 5) -- each fill as soon as the tensor core has consumed
+// the previous one (pe5_free).  Three of the four refills are far off the critical path; the fourth (tile 1's layer 0)
+// hides behind tile 1's views epilogue, which the layer-0 MMA has to wait for anyway.  The skip layer is issued
+// tile-major (tile 0: encoding block + 4 hidden blocks, then tile 1) with all 5 of its weight K-blocks resident.  With 5
+// slots a 4-block layer leaves one slot free, so the next layer's first K-block is prefetched a whole tile earlier: the
+// ~260-cycle wait of every layer's first MMA on the 4-slot ring goes away.
 template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold, int kEpiWarps, bool kPe1 = false>
 __global__ void __launch_bounds__(256 + 32 * kEpiWarps, 1)
 mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst_param) {
@@ -263,7 +263,6 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       mbar_init(sbase + L::a_ready + 8 * t, kEpiWarps * kCG);   // one arrive per epilogue warp (per CTA)
       mbar_init(sbase + L::pe_ready + 8 * t, 4 * kCG);    // one arrive per PE warp (per CTA)
       mbar_init(sbase + L::pe_free + 8 * t, 1);
-      mbar_init(sbase + L::tile_free + 8 * t, kEpiWarps);       // kPe1: this CTA's epilogue warps only
     }
     mbar_init(sbase + L::pe5_ready, 4 * kCG);
     mbar_init(sbase + L::pe5_free, 1);
@@ -315,7 +314,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             for (int t = 0; t < 2; ++t) {
               trace(1, 1, it, l, t);
               if (first_chunk) {
-                if (l == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
+                if (l == 0 && !kPe1) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
                 // a_ready[t] completes once per layer epilogue: phase index = seq - 1
                 if (seq != 0) mbar_wait(sbase + L::a_ready + 8 * t, (seq - 1) & 1, wc);
                 tc_fence_after();
@@ -336,11 +335,11 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
                 const int akb = unit_kb0(c) + kb;           // K-block index within the layer
                 uint32_t a_addr;
                 if (kPe1) {
-                  if (l == 5 && akb == 0) {                 // skip layer: the shared encoding buffer, this tile's fill
-                    mbar_wait(sbase + L::pe5_ready, (uint32_t)(2 * it + t) & 1, wc);
+                  if (l == 0 || (l == 5 && akb == 0)) {     // the shared encoding buffer: fill 4 it + (0,1: layer 0 | 2,3: skip layer)
+                    mbar_wait(sbase + L::pe5_ready, (uint32_t)(4 * it + (l == 0 ? 0 : 2) + t) & 1, wc);
                     tc_fence_after();
                     a_addr = sbase + L::pe0;
-                  } else {                                  // layer 0 reads the encoding from the tile's own first K-block
+                  } else {
                     a_addr = sbase + L::h0 + t * kHBytes + (l == 5 ? akb - 1 : akb) * kABlock;
                   }
                 } else if (l == 0 || (l == 5 && akb == 0)) a_addr = sbase + L::pe0 + t * kABlock;
@@ -351,7 +350,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
                 for (int k = 0; k < 4; ++k)                 // 4 x (K = 16) per 64-wide K-block: +32 B
                   umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (akb | k) != 0);
                 if (!kResident || t == 1) umma_commit<kCG>(sbase + L::w_empty + 8 * stage);
-                if (kPe1 && l == 5 && akb == 0) umma_commit<kCG>(sbase + L::pe5_free);   // encoding consumed: refill for the other tile
+                if (kPe1 && (l == 0 || (l == 5 && akb == 0))) umma_commit<kCG>(sbase + L::pe5_free);   // encoding consumed: next fill
               }
               if (last_chunk) umma_commit<kCG>(sbase + L::acc_full + 8 * t);
               if (!kPe1 && c == 5) umma_commit<kCG>(sbase + L::pe_free + 8 * t);
@@ -413,19 +412,25 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       }
     };
     if constexpr (kPe1) {
+      // fill k of the shared buffer (4 per iteration) may be written once the tensor core has consumed fill k - 1
+      uint32_t pk0[32], pk1[32];                                // both in-flight tiles' features stay in registers
+      uint32_t k = 0;
+      auto fill = [&](const uint32_t (&pk)[32]) {
+        if (k > 0) mbar_wait(sbase + L::pe5_free, (k - 1) & 1, wc);
+        put_pk(sbase + L::pe0, pk, sbase + L::pe5_ready);
+        ++k;
+      };
+      make_pk(0, 0, pk0);
+      make_pk(0, 1, pk1);
       for (int it = 0; it < iters; ++it) {
-        uint32_t pk0[32], pk1[32];                              // both in-flight tiles' features stay in registers
-        make_pk(it, 0, pk0);
-        if (it > 0) mbar_wait(sbase + L::tile_free + 0, (it - 1) & 1, wc);     // last iteration's views epilogue is done with h0[0]
-        put_pk(sbase + L::h0, pk0, sbase + L::pe_ready + 0);                   // layer 0 reads it from the tile's first K-block
-        make_pk(it, 1, pk1);
-        if (it > 0) mbar_wait(sbase + L::tile_free + 8, (it - 1) & 1, wc);
-        put_pk(sbase + L::h0 + kHBytes, pk1, sbase + L::pe_ready + 8);
-        // skip layer: the shared buffer, tile 0 then -- once the tensor core has consumed that -- tile 1
-        if (it > 0) mbar_wait(sbase + L::pe5_free, (uint32_t)(2 * it - 1) & 1, wc);
-        put_pk(sbase + L::pe0, pk0, sbase + L::pe5_ready);
-        mbar_wait(sbase + L::pe5_free, (uint32_t)(2 * it) & 1, wc);
-        put_pk(sbase + L::pe0, pk1, sbase + L::pe5_ready);
+        fill(pk0);                                              // layer 0, tile 0 (written a third of an iteration ahead)
+        fill(pk1);                                              // layer 0, tile 1
+        fill(pk0);                                              // skip layer, tile 0
+        fill(pk1);                                              // skip layer, tile 1
+        if (it + 1 < iters) {                                   // the next iteration's features while layers 5..9 run
+          make_pk(it + 1, 0, pk0);
+          make_pk(it + 1, 1, pk1);
+        }
       }
     } else {
       for (int it = 0; it < iters; ++it) {
@@ -564,9 +569,6 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (lane == 0) {
             if (kPair) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
             else mbar_arrive(sbase + L::a_ready + 8 * t);
-            // kPe1: after the views layer this warp no longer touches the tile's buffer (activations, head scratch):
-            // the PE warps of THIS CTA may write the next iteration's encoding into its first K-block
-            if (kPe1 && l == 9) mbar_arrive(sbase + L::tile_free + 8 * t);
             if (quad == 0) trace(3 + wg, 13, it, l, t);
           }
           if (kTrain && l < 9) {

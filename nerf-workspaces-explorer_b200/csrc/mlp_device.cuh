@@ -14,8 +14,8 @@ constexpr int kABlock = kTileM * 64 * 2;        // 16384: one [128 x 64] bf16 K-
 constexpr uint64_t kWaitTimeoutNs = 10ull * 1000 * 1000 * 1000;   // wall-clock bound of one barrier wait
 
 // kPeBufs: positional-encoding tiles held in shared memory -- 2 (one per in-flight tile, alive from layer 0 to the skip
-// layer) or 1 (kPe1 variant: layer 0 reads its encoding from the tile's own, still empty, activation buffer and the skip
-// layer from ONE shared buffer refilled from registers, which frees 16 KB for a fifth weight slot).
+// layer) or 1 (kPe1 variant: ONE buffer refilled from registers for each of its four uses per iteration, which frees
+// 16 KB for a fifth weight slot).
 template <bool kPair, int kStages, int kPeBufs = 2>
 struct SmemLayout {
   static constexpr uint32_t kStageBytes = kPair ? kKBlockBytes / 2 : kKBlockBytes;
@@ -31,10 +31,9 @@ struct SmemLayout {
   static constexpr uint32_t a_ready = acc_full + 16;
   static constexpr uint32_t pe_ready = a_ready + 16;
   static constexpr uint32_t pe_free = pe_ready + 16;
-  static constexpr uint32_t pe5_ready = pe_free + 16;      // kPe1: the shared skip-layer encoding buffer is filled / free
+  static constexpr uint32_t pe5_ready = pe_free + 16;      // kPe1: the shared encoding buffer is filled / consumed
   static constexpr uint32_t pe5_free = pe5_ready + 8;
-  static constexpr uint32_t tile_free = pe5_free + 8;      // kPe1: [2] this CTA's epilogue warps are done with tile t of the iteration
-  static constexpr uint32_t tmem_slot = tile_free + 16;
+  static constexpr uint32_t tmem_slot = pe5_free + 8;
   static constexpr uint32_t total = tmem_slot + 16;
   static constexpr uint32_t alloc_bytes = total + 1024;   // slack for manual 1024 B alignment
 };
