@@ -8,6 +8,7 @@
 //   coarse_z -> dirbias(coarse) -> MLP(coarse) -> composite -> sample_pdf+merge
 //            -> dirbias(fine)   -> MLP(fine)   -> composite (writes rgb and/or the uint8 pixels)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -115,6 +116,10 @@ extern "C" int nwx_ctx_create(int device, nwx_ctx** out) {
   nwx_ctx* c = new (std::nothrow) nwx_ctx();
   if (!c) return NWX_E_INVALID;
   c->device = device;
+  if (const char* v = getenv("NWX_MLP_VARIANT")) {       // A/B measurements of the MLP kernel variants (nwx_set_mlp_variant)
+    const int iv = atoi(v);
+    if (iv >= 0 && iv <= 4) c->mlp_variant = iv;
+  }
   // always-on diagnostics: survives a poisoned context because it lives in mapped host memory
   if (cudaHostAlloc(reinterpret_cast<void**>(&c->own_diag), 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess) {
     memset(c->own_diag, 0, 4 * sizeof(uint32_t));
@@ -158,7 +163,7 @@ extern "C" int nwx_load_weights(nwx_ctx* ctx, int which, const float* const* ten
 }
 
 extern "C" int nwx_set_mlp_variant(nwx_ctx* ctx, int variant) {
-  NWX_REQUIRE(ctx && variant >= 0 && variant <= 5);
+  NWX_REQUIRE(ctx && variant >= 0 && variant <= 4);
   ctx->mlp_variant = variant;
   return NWX_OK;
 }

@@ -192,20 +192,10 @@ __device__ __forceinline__ float epilogue_hidden(const MlpConsts& cst, int l, ui
   return f32x2_lo(sig) + f32x2_hi(sig);
 }
 
-// kPe1: ONE positional-encoding buffer instead of one per in-flight tile, a FIFTH weight slot in the 16 KB this frees.
-// The buffer is filled four times per iteration from the packed features the PE warps keep in registers -- tile 0 /
-// tile 1 for layer 0, tile 0 / tile 1 for the skip layer (l = 5) -- each fill as soon as the tensor core has consumed
-// the previous one (pe5_free).  Three of the four refills are far off the critical path; the fourth (tile 1's layer 0)
-// hides behind tile 1's views epilogue, which the layer-0 MMA has to wait for anyway.  The skip layer is issued
-// tile-major (tile 0: encoding block + 4 hidden blocks, then tile 1) with all 5 of its weight K-blocks resident.  With 5
-// slots a 4-block layer leaves one slot free, so the next layer's first K-block is prefetched a whole tile earlier: the
-// ~260-cycle wait of every layer's first MMA on the 4-slot ring goes away.
-template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold, int kEpiWarps, bool kPe1 = false>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain, bool kFold, int kEpiWarps>
 __global__ void __launch_bounds__(256 + 32 * kEpiWarps, 1)
 mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ MlpConsts cst_param) {
-  using L = SmemLayout<kPair, kStages, kPe1 ? 1 : 2>;
-  static_assert(!kPe1 || (kPair && kResident && kFold && !kTap && !kTrain && kStages == 5 && kEpiWarps == 8),
-                "kPe1 is written for the production configuration");
+  using L = SmemLayout<kPair, kStages>;
   const MlpConsts& cst = kTrain ? c_fwd_train_consts[args.which] : cst_param;
   // Timeline trace (debug instantiation only, nwx_debug_tap(ctx, -2, buf)): CTA 0 records
   // (tag, clock) pairs per role into buf[role][event][2] so the critical path can be read off.
@@ -225,12 +215,8 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
   constexpr int kW = 256 / kEpiGroups / 4;               // epilogue chunk width (32 or 16 columns)
   static_assert(kEpiWarps == 8 || kEpiWarps == 16, "8 or 16 epilogue warps");
   static_assert(!(kTrain && kEpiWarps != 8), "the training forward (masks, TMA tile stores) is written for 8 epilogue warps");
-  // kPe1 walks layers, not chunks: the skip layer is one unit of 5 K-blocks (9 units per tile with the fold)
-  constexpr int kNumChunks = kPe1 ? 9 : num_chunks<kFold>();
+  constexpr int kNumChunks = num_chunks<kFold>();
   constexpr int kSeqLen = layers_per_tile<kFold>();      // accumulator hand-offs per tile and iteration
-  auto unit_layer = [](int c) -> int { return kPe1 ? (c == 8 ? 9 : c) : chunk_layer<kFold>(c); };
-  auto unit_nkb = [](int c) -> int { return kPe1 ? (c == 0 ? 1 : (c == 5 ? 5 : 4)) : chunk_nkb(c); };
-  auto unit_kb0 = [](int c) -> int { return kPe1 ? 0 : chunk_kb0(c); };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -264,8 +250,6 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       mbar_init(sbase + L::pe_ready + 8 * t, 4 * kCG);    // one arrive per PE warp (per CTA)
       mbar_init(sbase + L::pe_free + 8 * t, 1);
     }
-    mbar_init(sbase + L::pe5_ready, 4 * kCG);
-    mbar_init(sbase + L::pe5_free, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kCG>(sbase + L::tmem_slot, 512);
@@ -281,17 +265,17 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       uint32_t fill = 0;
       for (int it = 0; it < iters; ++it) {
         for (int c = 0; c < kNumChunks; ++c) {
-          const int l = unit_layer(c);
+          const int l = chunk_layer<kFold>(c);
           const uint32_t bytes = (l == 9 ? kKBlockBytes / 2 : kKBlockBytes) / kCG;
           for (int t = 0; t < (kResident ? 1 : 2); ++t) {
-            for (int kb = 0; kb < unit_nkb(c); ++kb, ++fill) {
+            for (int kb = 0; kb < chunk_nkb(c); ++kb, ++fill) {
               const uint32_t stage = fill % kStages, round = fill / kStages;
               trace(0, 31, it, l, kb);
               mbar_wait(sbase + L::w_empty + 8 * stage, (round & 1) ^ 1, wc);
               trace(0, 32, it, l, kb);
               const uint32_t bar = sbase + L::w_full + 8 * stage;
               mbar_arrive_expect_tx(bar, bytes);
-              const uint8_t* src = args.wimg + kblock_offset(layer_gkb0<kFold>(l) + unit_kb0(c) + kb) + rank * bytes;
+              const uint8_t* src = args.wimg + kblock_offset(layer_gkb0<kFold>(l) + chunk_kb0(c) + kb) + rank * bytes;
               bulk_g2s(sbase + L::w0 + stage * L::kStageBytes, src, bytes, bar);
             }
           }
@@ -306,15 +290,15 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
       if (rank == 0) {
         for (int it = 0; it < iters; ++it) {
           for (int c = 0; c < kNumChunks; ++c) {
-            const int l = unit_layer(c);
-            const int nkb = unit_nkb(c);
+            const int l = chunk_layer<kFold>(c);
+            const int nkb = chunk_nkb(c);
             const uint32_t seq = (uint32_t)it * kSeqLen + layer_seq<kFold>(l);   // index of this accumulator hand-off
-            const bool first_chunk = kPe1 || (c != 6), last_chunk = kPe1 || (c != 5);
+            const bool first_chunk = (c != 6), last_chunk = (c != 5);
             const uint32_t idesc = umma_idesc_bf16(kTileM * kCG, l == 9 ? kViewHidden : kHidden);
             for (int t = 0; t < 2; ++t) {
               trace(1, 1, it, l, t);
               if (first_chunk) {
-                if (l == 0 && !kPe1) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
+                if (l == 0) mbar_wait(sbase + L::pe_ready + 8 * t, it & 1, wc);
                 // a_ready[t] completes once per layer epilogue: phase index = seq - 1
                 if (seq != 0) mbar_wait(sbase + L::a_ready + 8 * t, (seq - 1) & 1, wc);
                 tc_fence_after();
@@ -332,17 +316,9 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
                   if (kPair) mbar_wait(sbase + L::w_peer + 8 * stage, round & 1, wc);
                   tc_fence_after();
                 }
-                const int akb = unit_kb0(c) + kb;           // K-block index within the layer
+                const int akb = chunk_kb0(c) + kb;          // K-block index within the layer
                 uint32_t a_addr;
-                if (kPe1) {
-                  if (l == 0 || (l == 5 && akb == 0)) {     // the shared encoding buffer: fill 4 it + (0,1: layer 0 | 2,3: skip layer)
-                    mbar_wait(sbase + L::pe5_ready, (uint32_t)(4 * it + (l == 0 ? 0 : 2) + t) & 1, wc);
-                    tc_fence_after();
-                    a_addr = sbase + L::pe0;
-                  } else {
-                    a_addr = sbase + L::h0 + t * kHBytes + (l == 5 ? akb - 1 : akb) * kABlock;
-                  }
-                } else if (l == 0 || (l == 5 && akb == 0)) a_addr = sbase + L::pe0 + t * kABlock;
+                if (l == 0 || (l == 5 && akb == 0)) a_addr = sbase + L::pe0 + t * kABlock;
                 else a_addr = sbase + L::h0 + t * kHBytes + (l == 5 ? akb - 1 : akb) * kABlock;
                 const uint64_t adesc = umma_desc_k_sw128(a_addr);
                 const uint64_t bdesc = umma_desc_k_sw128(sbase + L::w0 + stage * L::kStageBytes);
@@ -350,10 +326,9 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
                 for (int k = 0; k < 4; ++k)                 // 4 x (K = 16) per 64-wide K-block: +32 B
                   umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (akb | k) != 0);
                 if (!kResident || t == 1) umma_commit<kCG>(sbase + L::w_empty + 8 * stage);
-                if (kPe1 && (l == 0 || (l == 5 && akb == 0))) umma_commit<kCG>(sbase + L::pe5_free);   // encoding consumed: next fill
               }
               if (last_chunk) umma_commit<kCG>(sbase + L::acc_full + 8 * t);
-              if (!kPe1 && c == 5) umma_commit<kCG>(sbase + L::pe_free + 8 * t);
+              if (c == 5) umma_commit<kCG>(sbase + L::pe_free + 8 * t);
               trace(1, 3, it, l, t);
             }
             if (kResident) fill += nkb;
@@ -374,80 +349,51 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
     // ============================================================ PE producers ====
     const WaitCtx wc{args.diag, 0x300u};
     const int row = (warp - 4) * 32 + lane;
-    // 63 features (+ zero pad) of this thread's point of tile (it, t) as 32 packed bf16 pairs
-    auto make_pk = [&](int it, int t, uint32_t (&pk)[32]) {
-      int64_t p = tile_of(it, t) * kTileM + row;
-      if (p >= P) p = P - 1;                                  // tail tile: recompute a valid point
-      if (args.embedded) {                                    // features are read, not computed
-        const float* e = args.embedded + p * (kPeXyz + kPeDir);
-#pragma unroll
-        for (int i = 0; i < 31; ++i) pk[i] = pack_bf16x2(__ldg(e + 2 * i), __ldg(e + 2 * i + 1));
-        pk[31] = pack_bf16x2(__ldg(e + 62), 0.0f);
-        return;
-      }
-      float px, py, pz;
-      if (args.pts) {
-        px = __ldg(args.pts + p * 3 + 0); py = __ldg(args.pts + p * 3 + 1); pz = __ldg(args.pts + p * 3 + 2);
-      } else {
-        const int64_t ray = (p >> 32) == 0 ? (int64_t)((uint32_t)p / (uint32_t)args.S) : p / args.S;   // 32-bit divide when it fits
-        const float* r = args.rays + ray * args.ray_dim;
-        const float zz = __ldg(args.z + p);
-        px = __fadd_rn(__ldg(r + 0), __fmul_rn(__ldg(r + 3), zz));   // inference handler:223
-        py = __fadd_rn(__ldg(r + 1), __fmul_rn(__ldg(r + 4), zz));
-        pz = __fadd_rn(__ldg(r + 2), __fmul_rn(__ldg(r + 5), zz));
-      }
-      encode_point(px, py, pz, pk);
-    };
-    // one [128 x 64] bf16 K-block row of this thread, 128-byte swizzled, then "my warp's rows are in place"
-    auto put_pk = [&](uint32_t tile_base, const uint32_t (&pk)[32], uint32_t ready_bar) {
-      const uint32_t dst = tile_base + row * 128;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        st_shared_v4(dst + ((j ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(leader(ready_bar));
-        else mbar_arrive(ready_bar);
-      }
-    };
-    if constexpr (kPe1) {
-      // fill k of the shared buffer (4 per iteration) may be written once the tensor core has consumed fill k - 1
-      uint32_t pk0[32], pk1[32];                                // both in-flight tiles' features stay in registers
-      uint32_t k = 0;
-      auto fill = [&](const uint32_t (&pk)[32]) {
-        if (k > 0) mbar_wait(sbase + L::pe5_free, (k - 1) & 1, wc);
-        put_pk(sbase + L::pe0, pk, sbase + L::pe5_ready);
-        ++k;
-      };
-      make_pk(0, 0, pk0);
-      make_pk(0, 1, pk1);
-      for (int it = 0; it < iters; ++it) {
-        fill(pk0);                                              // layer 0, tile 0 (written a third of an iteration ahead)
-        fill(pk1);                                              // layer 0, tile 1
-        fill(pk0);                                              // skip layer, tile 0
-        fill(pk1);                                              // skip layer, tile 1
-        if (it + 1 < iters) {                                   // the next iteration's features while layers 5..9 run
-          make_pk(it + 1, 0, pk0);
-          make_pk(it + 1, 1, pk1);
+    for (int it = 0; it < iters; ++it) {
+      for (int t = 0; t < 2; ++t) {
+        int64_t p = tile_of(it, t) * kTileM + row;
+        if (p >= P) p = P - 1;                                  // tail tile: recompute a valid point
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (args.embedded) {
+          // handled below: features are read, not computed
+        } else if (args.pts) {
+          px = __ldg(args.pts + p * 3 + 0); py = __ldg(args.pts + p * 3 + 1); pz = __ldg(args.pts + p * 3 + 2);
+        } else {
+          const int64_t ray = (p >> 32) == 0 ? (int64_t)((uint32_t)p / (uint32_t)args.S) : p / args.S;   // 32-bit divide when it fits
+          const float* r = args.rays + ray * args.ray_dim;
+          const float zz = __ldg(args.z + p);
+          px = __fadd_rn(__ldg(r + 0), __fmul_rn(__ldg(r + 3), zz));   // inference handler:223
+          py = __fadd_rn(__ldg(r + 1), __fmul_rn(__ldg(r + 4), zz));
+          pz = __fadd_rn(__ldg(r + 2), __fmul_rn(__ldg(r + 5), zz));
         }
-      }
-    } else {
-      for (int it = 0; it < iters; ++it) {
-        for (int t = 0; t < 2; ++t) {
-          uint32_t pk[32];
-          make_pk(it, t, pk);
-          if (row == 0) trace(2, 21, it, 0, t);
-          if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
-          if (row == 0) trace(2, 22, it, 0, t);
-          put_pk(sbase + L::pe0 + t * kABlock, pk, sbase + L::pe_ready + 8 * t);
-          if (kTrain && args.acts != nullptr && tile_of(it, t) < args.n_tiles) {
-            uint8_t* g = args.acts + tile_img_offset(act_slot_kb0(0), 1, args.n_tiles, tile_of(it, t), 0) + row * 128;
+        uint32_t pk[32];
+        if (args.embedded) {
+          const float* e = args.embedded + p * (kPeXyz + kPeDir);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(g + ((j ^ (row & 7)) << 4)) =
-                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          for (int i = 0; i < 31; ++i) pk[i] = pack_bf16x2(__ldg(e + 2 * i), __ldg(e + 2 * i + 1));
+          pk[31] = pack_bf16x2(__ldg(e + 62), 0.0f);
+        } else {
+          encode_point(px, py, pz, pk);
+        }
+        if (row == 0) trace(2, 21, it, 0, t);
+        if (it > 0) mbar_wait(sbase + L::pe_free + 8 * t, (it - 1) & 1, wc);
+        if (row == 0) trace(2, 22, it, 0, t);
+        const uint32_t dst = sbase + L::pe0 + t * kABlock + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(dst + ((j ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(leader(sbase + L::pe_ready + 8 * t));
+          else mbar_arrive(sbase + L::pe_ready + 8 * t);
+        }
+        if (kTrain && args.acts != nullptr && tile_of(it, t) < args.n_tiles) {
+          uint8_t* g = args.acts + tile_img_offset(act_slot_kb0(0), 1, args.n_tiles, tile_of(it, t), 0) + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(g + ((j ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
     }
@@ -774,11 +720,10 @@ int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t 
   return NWX_OK;
 }
 
-template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false, bool kFold = false, int kEpiWarps = 8,
-          bool kPe1 = false>
+template <bool kPair, bool kResident, int kStages, bool kTap, bool kTrain = false, bool kFold = false, int kEpiWarps = 8>
 static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
-  using Lay = SmemLayout<kPair, kStages, kPe1 ? 1 : 2>;
-  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain, kFold, kEpiWarps, kPe1>;
+  using Lay = SmemLayout<kPair, kStages>;
+  auto kern = mlp_fused_kernel<kPair, kResident, kStages, kTap, kTrain, kFold, kEpiWarps>;
   static PerDeviceOnce configured;                 // the attribute is per device
   const int dev = current_device();
   if (configured.need(dev)) {
@@ -814,8 +759,7 @@ static int launch_variant(const PackedNet& net, MlpArgs args, cudaStream_t st) {
 }
 
 // variant: 0/1 = CTA pair + resident weights + folded feature layer (production), 2 = CTA pair streaming,
-//          3 = single CTA streaming (cta_group::1), 4 = as 1 with the reference's layer structure (no fold),
-//          5 = as 1 with ONE positional-encoding buffer and a fifth weight slot (kPe1)
+//          3 = single CTA streaming (cta_group::1), 4 = as 1 with the reference's layer structure (no fold)
 int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st) {
   if (args.P <= 0) return NWX_OK;
   const bool tap = args.dbg_out != nullptr;
@@ -826,8 +770,6 @@ int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st)
     case 4: return tap ? launch_variant<true, true, 4, true>(net, args, st) : launch_variant<true, true, 4, false>(net, args, st);
     case 2: return tap ? launch_variant<true, false, 4, true>(net, args, st) : launch_variant<true, false, 4, false>(net, args, st);
     case 3: return tap ? launch_variant<false, false, 2, true>(net, args, st) : launch_variant<false, false, 2, false>(net, args, st);
-    case 5: return tap ? launch_variant<true, true, 4, true, false, true>(net, args, st)      // taps / traces: the 4-slot kernel
-                       : launch_variant<true, true, 5, false, false, true, 8, true>(net, args, st);
     default: return NWX_E_INVALID;
   }
 }

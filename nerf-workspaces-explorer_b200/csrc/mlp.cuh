@@ -97,7 +97,7 @@ struct MlpArgs {
 int pack_network(PackedNet& net, const float* const* tensors, cudaStream_t st);
 int pack_network_images(PackedNet& net, const float* const* tensors, bool with_fold, cudaStream_t st,
                         uint8_t* fold_t = nullptr);
-inline bool variant_folds(int variant) { return variant <= 1 || variant == 5; }
+inline bool variant_folds(int variant) { return variant <= 1; }
 int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, bool fold,
                    float* out, cudaStream_t st);
 int launch_mlp(const PackedNet& net, MlpArgs args, int variant, cudaStream_t st);

@@ -13,15 +13,12 @@ constexpr int kHBytes = kTileM * kHidden * 2;   // 65536: one activation tile, 4
 constexpr int kABlock = kTileM * 64 * 2;        // 16384: one [128 x 64] bf16 K-block of A
 constexpr uint64_t kWaitTimeoutNs = 10ull * 1000 * 1000 * 1000;   // wall-clock bound of one barrier wait
 
-// kPeBufs: positional-encoding tiles held in shared memory -- 2 (one per in-flight tile, alive from layer 0 to the skip
-// layer) or 1 (kPe1 variant: ONE buffer refilled from registers for each of its four uses per iteration, which frees
-// 16 KB for a fifth weight slot).
-template <bool kPair, int kStages, int kPeBufs = 2>
+template <bool kPair, int kStages>
 struct SmemLayout {
   static constexpr uint32_t kStageBytes = kPair ? kKBlockBytes / 2 : kKBlockBytes;
   static constexpr uint32_t h0 = 0;
   static constexpr uint32_t pe0 = 2 * kHBytes;
-  static constexpr uint32_t w0 = pe0 + kPeBufs * kABlock;
+  static constexpr uint32_t w0 = pe0 + 2 * kABlock;
   static constexpr uint32_t bar0 = w0 + kStages * kStageBytes;
   // barrier slots (8 B each)
   static constexpr uint32_t w_full = bar0;
@@ -31,9 +28,7 @@ struct SmemLayout {
   static constexpr uint32_t a_ready = acc_full + 16;
   static constexpr uint32_t pe_ready = a_ready + 16;
   static constexpr uint32_t pe_free = pe_ready + 16;
-  static constexpr uint32_t pe5_ready = pe_free + 16;      // kPe1: the shared encoding buffer is filled / consumed
-  static constexpr uint32_t pe5_free = pe5_ready + 8;
-  static constexpr uint32_t tmem_slot = pe5_free + 8;
+  static constexpr uint32_t tmem_slot = pe_free + 16;
   static constexpr uint32_t total = tmem_slot + 16;
   static constexpr uint32_t alloc_bytes = total + 1024;   // slack for manual 1024 B alignment
 };

@@ -15,7 +15,7 @@ fx, fy, cx, cy = synthetic.intrinsics(H, W)
 rays = eng.raygen(synthetic.sweep_poses(1, 0), H, W, fx, fy, cx, cy, 0.1, 10.0)
 z = torch.sort(torch.rand(H * W, 192, device=dev) * 9.9 + 0.1, -1)[0]
 res = {}
-for v in [int(a) for a in sys.argv[1:]] or [1, 5, 1, 5]:
+for v in [int(a) for a in sys.argv[1:]] or [1, 2, 3, 4]:
     eng.set_mlp_variant(v)
     for _ in range(2):
         eng.mlp_forward(E.FINE, rays, z)
