@@ -4,8 +4,10 @@ and against the gradients the reference's own autograd produced (tests/golden/tr
 
 Tolerance: the backward runs its GEMMs on bf16 tensor-core operands (activations and back-propagated
 gradients are rounded to bf16 per layer, fp32 accumulation), the reference in fp32.  Stated bar:
-losses within 1e-5 relative, every gradient tensor within 5 % in norm and cosine >= 0.99 with the
-fp32 gradient, the heads (fp32 CUDA-core path) cosine >= 0.9999."""
+losses within 1e-5 relative, every gradient tensor within 3 % in norm and cosine >= 0.993 with the
+fp32 gradient (measured on the 96-ray batch: worst 1.3 % and 0.9955, both on the layers farthest from the
+loss, _pts_linears.0 of the coarse network), the heads (fp32 CUDA-core path) cosine >= 0.9999.  The outcome of
+an optimisation run against fp32 autograd is tests/test_gpu_trained.py."""
 import json
 import os
 import subprocess
@@ -36,8 +38,10 @@ def test_training_step_isolated_first():
     assert r["ok"], r
     for a, b in zip(r["loss"], r["loss_ref"]):
         assert abs(a - b) <= 1e-5 * abs(b), r
+    worst = (max(abs(v[0] - 1.0) for v in r["tensors"].values()), min(v[1] for v in r["tensors"].values()))
+    print(f"gradients vs fp32 autograd: worst |norm ratio - 1| {worst[0]:.4f}, worst cosine {worst[1]:.5f}")
     for name, (ratio, cos, finite) in r["tensors"].items():
-        assert finite and abs(ratio - 1.0) <= 0.05 and cos >= 0.99, (name, ratio, cos)
+        assert finite and abs(ratio - 1.0) <= 0.03 and cos >= 0.993, (name, ratio, cos)
         if "alpha" in name or "rgb" in name:
             assert cos >= 0.9999, (name, cos)
 
