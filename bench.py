@@ -207,7 +207,7 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------- GPU arm ----
-NCU_MLP_CAPTURE = os.path.join("profiles", "r01_ncu_mlp_full_fold.csv")
+NCU_MLP_CAPTURE = os.path.join("profiles", "r02_ncu_mlp_full.csv")
 
 
 def mlp_dram_traffic_per_step():
