@@ -130,12 +130,15 @@ __device__ __forceinline__ float ray_dnorm(const float* __restrict__ rays_d, int
 //     global wavefronts: the direct version below needs 32 L1 wavefronts per LDG.128 (each lane in its own
 //     128-byte line) -- ~210 per fine ray, which is what bounded it at 0.37 ms per frame.
 //   * direct: per-lane __ldg of the same runs (any alignment, any S); also the A/B baseline (NWX_COMPOSITE=direct).
-template <int K>
+// LPR = lanes per ray: 32 (one ray per warp) or 16 (two rays per warp: the per-ray part -- one scan, five sums, the
+// output tail -- is shared by both halves of the warp, which is what a 64-sample coarse pass is made of); `lane` is
+// the lane's index within its ray's LPR lanes, `live` is false for the missing second ray of an odd tail.
+template <int K, int LPR = 32>
 __device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float (&zr)[K + 1], const float (&nz)[K], bool noisy,
                                               int64_t ray, int S, int lane, float dnorm,
                                               int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
                                               float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
-                                              uint8_t* __restrict__ rgb8, int& bad) {
+                                              uint8_t* __restrict__ rgb8, int& bad, bool live = true) {
   const int s0 = lane * K;
   const int64_t base = ray * S;
   float alpha[K];
@@ -154,8 +157,13 @@ __device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float
     tloc[j] = p;
     p *= (double)t;
   }
-  const double incl = warp_incl_prod(p, lane);                // :75 cumprod (exclusive), fp64 like torch
-  double excl = __shfl_up_sync(kFull, incl, 1);
+  double incl = p;                                            // :75 cumprod (exclusive), fp64 like torch
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) {
+    const double up = __shfl_up_sync(kFull, incl, o, LPR);
+    if (lane >= o) incl *= up;
+  }
+  double excl = __shfl_up_sync(kFull, incl, 1, LPR);
   if (lane == 0) excl = 1.0;
   float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
 #pragma unroll
@@ -164,7 +172,7 @@ __device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float
     const float T = (float)(excl * tloc[j]);
     const float w = __fmul_rn(alpha[j], T);
     if (s < S) {
-      if (weights) weights[base + s] = w;
+      if (weights && live) weights[base + s] = w;
       a_r += __fmul_rn(w, sigmoidf_fast(rw[j].x));                        // :62,:84
       a_g += __fmul_rn(w, sigmoidf_fast(rw[j].y));
       a_b += __fmul_rn(w, sigmoidf_fast(rw[j].z));
@@ -172,9 +180,12 @@ __device__ __forceinline__ void composite_ray(const float4 (&rw)[K], const float
       a_w += w;
     }
   }
-  a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);        // :84
-  a_d = warp_sum(a_d); a_w = warp_sum(a_w);                             // :93,:95
-  if (lane == 0) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {                              // :84, :93, :95 (xor butterflies stay inside the ray's lanes)
+    a_r += __shfl_xor_sync(kFull, a_r, o); a_g += __shfl_xor_sync(kFull, a_g, o); a_b += __shfl_xor_sync(kFull, a_b, o);
+    a_d += __shfl_xor_sync(kFull, a_d, o); a_w += __shfl_xor_sync(kFull, a_w, o);
+  }
+  if (lane == 0 && live) {
     const float q = __fdiv_rn(a_d, a_w);                               // :94; 0/0 = NaN on empty rays and
     const float dspv = __fdiv_rn(1.0f, (q != q) ? q : fmaxf(1e-10f, q));   // torch.max propagates NaN
     if (white_bkgd) {                                                   // :98
@@ -295,7 +306,85 @@ composite_fwd_bulk_kernel(const float* __restrict__ raw, const float* __restrict
   if (flags && bad) atomicOr(flags, bad);
 }
 
+// Bulk front end, TWO rays per warp (16 lanes x K samples each) for short rays (S <= 64: the coarse pass).  The two rays
+// are neighbours in memory, so one pair of bulk copies brings both.  Same arithmetic per ray as the kernel above (a
+// lane's run of K samples starts at a different sample, so sums associate differently: outputs agree to rounding,
+// weights -- a function of the fp64 scan -- are identical).
+template <int K>
+__global__ void __launch_bounds__(kCompWarps * 32, 4)
+composite_fwd_bulk2_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                           const float* __restrict__ rays_d, int d_stride, const float* __restrict__ noise,
+                           const RngSpec rng, int64_t N, int S, int white_bkgd, float* __restrict__ rgb, float* __restrict__ disp,
+                           float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
+                           int32_t* __restrict__ flags, uint8_t* __restrict__ rgb8) {
+  __shared__ __align__(128) float4 s_raw[kCompWarps][2 * K * 16];
+  __shared__ __align__(16) float s_z[kCompWarps][2 * K * 16];
+  __shared__ __align__(8) uint64_t s_bar[kCompWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, sl = lane & 15;
+  const int64_t pairs = (N + 1) >> 1;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const bool noisy = noise != nullptr || rng.on;
+  const int s0 = sl * K;
+  const uint32_t bar = smem_u32(&s_bar[wib]), dst_raw = smem_u32(&s_raw[wib][0]), dst_z = smem_u32(&s_z[wib][0]);
+  const WaitCtx wc{nullptr, 0x5200u};
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  auto fetch = [&](int64_t pair) {                              // lane 0: both rays' bytes are contiguous in HBM
+    const uint32_t n = (2 * pair + 1 < N) ? 2u : 1u;
+    mbar_arrive_expect_tx(bar, n * (uint32_t)S * 20u);
+    bulk_g2s(dst_raw, raw + 2 * pair * S * 4, n * (uint32_t)S * 16u, bar);
+    bulk_g2s(dst_z, z + 2 * pair * S, n * (uint32_t)S * 4u, bar);
+  };
+  if (warp0 < pairs && lane == 0) fetch(warp0);
+  uint32_t phase = 0;
+  int bad = 0;
+  for (int64_t pair = warp0; pair < pairs; pair += nwarps) {
+    const int64_t ray_raw = 2 * pair + half;
+    const bool live = ray_raw < N;
+    const int64_t ray = live ? ray_raw : N - 1;                 // the missing twin of an odd tail recomputes its neighbour
+    const int64_t base = ray * S;
+    float zr[K + 1], nz[K];
+    float4 rw[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int s = s0 + j;
+      const int64_t idx = base + (s < S ? s : S - 1);
+      nz[j] = noise ? __ldg(noise + idx) : (rng.on ? rng_normal(rng, (uint64_t)idx) : 0.0f);
+    }
+    const float dnorm = ray_dnorm(rays_d, d_stride, ray);
+    mbar_wait(bar, phase, wc);
+    phase ^= 1u;
+    const int hoff = (live ? half : 0) * S;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int s = s0 + j, sc = s < S ? s : S - 1;
+      rw[j] = s_raw[wib][hoff + sc];
+      zr[j] = s_z[wib][hoff + sc];
+    }
+    zr[K] = __shfl_down_sync(kFull, zr[0], 1);                  // lane 15 / 31 get a foreign value: their last sample has dist 1e10
+    __syncwarp();
+    if (lane == 0 && pair + nwarps < pairs) {
+      fence_proxy_async_smem();
+      fetch(pair + nwarps);
+    }
+    composite_ray<K, 16>(rw, zr, nz, noisy, ray, S, sl, dnorm, white_bkgd, rgb, disp, acc, depth, weights, rgb8, bad, live);
+  }
+  if (flags && bad) atomicOr(flags, bad);
+}
+
 // NWX_COMPOSITE=direct forces the per-lane global loads (A/B measurements)
+static bool composite_two_rays_enabled() {      // NWX_COMPOSITE=one_ray: one ray per warp also for short rays (A/B)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("NWX_COMPOSITE");
+    on = (e && strcmp(e, "one_ray") == 0) ? 0 : 1;
+  }
+  return on == 1;
+}
 static bool composite_bulk_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -388,7 +477,15 @@ int nwx::launch_composite_fwd(const float* raw, const float* z, const float* ray
   NWX_REQUIRE(raw && z && rays_d && (rgb || rgb8));
   const bool bulk = nwx::composite_bulk_enabled() && (S % 4) == 0 && ((reinterpret_cast<uintptr_t>(raw) & 15u) == 0) &&
                     ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
-  if (bulk) {
+  if (bulk && S <= 64 && nwx::composite_two_rays_enabled()) {        // short rays: two per warp, K = ceil(S / 16) <= 4
+    const unsigned grid = nwx::comp_grid((N + 1) / 2);
+    switch ((S + 15) / 16) {
+      case 1: nwx::composite_fwd_bulk2_kernel<1><<<grid, nwx::kCompWarps * 32, 0, st>>>(raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8); break;
+      case 2: nwx::composite_fwd_bulk2_kernel<2><<<grid, nwx::kCompWarps * 32, 0, st>>>(raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8); break;
+      case 3: nwx::composite_fwd_bulk2_kernel<3><<<grid, nwx::kCompWarps * 32, 0, st>>>(raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8); break;
+      default: nwx::composite_fwd_bulk2_kernel<4><<<grid, nwx::kCompWarps * 32, 0, st>>>(raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8); break;
+    }
+  } else if (bulk) {
     NWX_DISPATCH_K(S, (nwx::composite_fwd_bulk_kernel<K><<<nwx::comp_grid(N), nwx::kCompWarps * 32, 0, st>>>(
                           raw, z, rays_d, d_stride, noise, rng, N, S, white_bkgd, rgb, disp, acc, depth, weights, flags, rgb8)));
   } else {
