@@ -176,7 +176,8 @@ class NeRFReplicaInferenceHandler:
         if (self.use_cuda_graphs and out is None and not eng.profiling and 0 < count <= self.max_rays_per_launch
                 and not torch.cuda.is_current_stream_capturing()):
             key = (int(c2w_dev.shape[0]), int(ray0), int(count), self._img_h, self._img_w, self._fx, self._fy, self._cx,
-                   self._cy, self._n_samples, self._n_importance, self._white_bkgd)
+                   self._cy, self._depth_close_bound, self._depth_far_bound, self._n_samples, self._n_importance,
+                   self._white_bkgd, self.max_rays_per_launch)       # everything the captured launches bake in
             g = self._graphs.get(key)
             if g is not None and g.stamp != (eng.weights_version, eng.scratch_state()[1]):
                 g = None                              # weights reloaded or scratch re-allocated since the capture
