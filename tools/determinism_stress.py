@@ -37,9 +37,18 @@ def main():
         "mlp_coarse": lambda: eng.mlp_forward(E.COARSE, rays, z_c).reshape(-1),
         "render_rays_rgb": lambda: eng.render_rays(rays, want=("rgb_fine",))["rgb_fine"].reshape(-1),
     }
+    # the shard shapes of tests/test_gpu_render.py::test_full_frame_properties_640x480 (row tiles + a ragged cut):
+    # small and odd launches exercise the kernels' tails; each must reproduce its slice of the full frame
+    full = eng.render_rays(rays, want=("rgb_fine",))["rgb_fine"].clone()
+    cuts = [0, 100 * W, 100 * W + 77, 300 * W, H * W]
+
+    def shards():
+        parts = [eng.render_rays(rays[a:b], want=("rgb_fine",))["rgb_fine"] for a, b in zip(cuts[:-1], cuts[1:])]
+        return torch.cat(parts, 0).reshape(-1)
+    cases["sharded_render_vs_full_frame"] = shards
     res = {}
     for name, fn in cases.items():
-        ref = fn().clone()
+        ref = full.reshape(-1) if name.startswith("sharded") else fn().clone()
         bad, worst = 0, 0
         for _ in range(args.iters):
             cur = fn()
