@@ -37,6 +37,10 @@ struct nwx_ctx {
   float* partial = nullptr;      // [n_partials][NWX_PARAMS_PER_NET], zero-initialised once
   double* loss_scratch = nullptr;   // ticket + per-block partial sums of the MSE kernel, zero-initialised once
   int n_partials = 0;
+  // training: the head kernels of each network's backward run on this stream, underneath its dW kernel
+  cudaStream_t heads_stream = nullptr;
+  cudaEvent_t ev_heads_fork[2] = {}, ev_heads_join[2] = {};
+  bool heads_on_side_stream = true;          // NWX_TRAIN_HEADS_STREAM=0: on the caller's stream (A/B)
   bool profiling = false;
   bool ev_recorded = false;
   cudaEvent_t ev[NWX_NUM_STAGES + 1] = {};
@@ -116,6 +120,7 @@ extern "C" int nwx_ctx_create(int device, nwx_ctx** out) {
   nwx_ctx* c = new (std::nothrow) nwx_ctx();
   if (!c) return NWX_E_INVALID;
   c->device = device;
+  if (const char* v = getenv("NWX_TRAIN_HEADS_STREAM")) c->heads_on_side_stream = atoi(v) != 0;
   if (const char* v = getenv("NWX_MLP_VARIANT")) {       // A/B measurements of the MLP kernel variants (nwx_set_mlp_variant)
     const int iv = atoi(v);
     if (iv >= 0 && iv <= 4) c->mlp_variant = iv;
@@ -151,6 +156,11 @@ extern "C" int nwx_ctx_destroy(nwx_ctx* ctx) {
   }
   for (auto e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->heads_stream) cudaStreamDestroy(ctx->heads_stream);
+  for (int w = 0; w < 2; ++w) {
+    if (ctx->ev_heads_fork[w]) cudaEventDestroy(ctx->ev_heads_fork[w]);
+    if (ctx->ev_heads_join[w]) cudaEventDestroy(ctx->ev_heads_join[w]);
+  }
   if (ctx->own_diag) cudaFreeHost(ctx->own_diag);
   delete ctx;
   return NWX_OK;
@@ -461,6 +471,13 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     NWX_CUDA_TRY(cudaMalloc(&ctx->partial, bytes));
     NWX_CUDA_TRY(cudaMemsetAsync(ctx->partial, 0, bytes, st));
   }
+  if (ctx->heads_on_side_stream && !ctx->heads_stream) {
+    NWX_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->heads_stream, cudaStreamNonBlocking));
+    for (int w = 0; w < 2; ++w) {
+      NWX_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_heads_fork[w], cudaEventDisableTiming));
+      NWX_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_heads_join[w], cudaEventDisableTiming));
+    }
+  }
   if (!ctx->loss_scratch) {
     NWX_CUDA_TRY(cudaMalloc(&ctx->loss_scratch, nwx::kMseScratchBytes));
     NWX_CUDA_TRY(cudaMemsetAsync(ctx->loss_scratch, 0, nwx::kMseScratchBytes, st));
@@ -524,7 +541,8 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     b.pe_dir = pe_dir; b.grad = grads[w]; b.diag = ctx->diag; b.P = N * S[w]; b.S = S[w]; b.max_partials = ctx->n_partials;
     b.which = w;
     b.experiment = ctx->experiment;
-    if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st))) return rc;
+    if ((rc = nwx::launch_mlp_backward(ctx->net[w], b, st, ctx->heads_on_side_stream ? ctx->heads_stream : nullptr,
+                                       ctx->ev_heads_fork[w], ctx->ev_heads_join[w]))) return rc;
     // data-parallel callers all-reduce the coarse network's gradients underneath the fine network's backward
     if (w == 0 && io->ev_coarse_done) NWX_CUDA_TRY(cudaEventRecord((cudaEvent_t)io->ev_coarse_done, st));
   }

@@ -131,7 +131,8 @@ inline size_t mask_image_bytes(int64_t n_tiles) { return (size_t)(n_tiles + 1) *
 const int* flat_offsets();
 size_t packed_transposed_bytes();
 int train_pack(PackedNet& net, const float* params_flat, cudaStream_t st);
-int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st);
+int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st, cudaStream_t heads_st = nullptr,
+                        cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 constexpr int kMseMaxBlocks = 512;
 constexpr size_t kMseScratchBytes = (1 + 2 * kMseMaxBlocks) * sizeof(double);   // ticket word + per-block partial sums
 int launch_mse_grad(const float* rgb_c, const float* rgb_f, const float* gt, int64_t n_rays, float* d_c, float* d_f,

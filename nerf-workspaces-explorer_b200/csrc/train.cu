@@ -1059,7 +1059,8 @@ size_t head_partial_bytes(int64_t n_tiles, int64_t n_rays, int S) {
 size_t grad_image_bytes(int64_t n_tiles) { return (size_t)kGradKBlocksPerTile * (n_tiles + 1) * kTileImgBytes; }
 
 // Backward of one network: d_raw [P,4] -> flat gradient buffer `grad` (state_dict order, += into it).
-int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st) {
+int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_t st, cudaStream_t heads_st,
+                        cudaEvent_t fork, cudaEvent_t join) {
   if (a.P <= 0) return NWX_OK;
   const int64_t tiles = (a.P + kTileM - 1) / kTileM;
   // ---- dX ----
@@ -1086,6 +1087,37 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
     cfg.attrs = attr; cfg.numAttrs = 1;
     NWX_CUDA_TRY(cudaLaunchKernelEx(&cfg, mlp_bwd_dx_kernel, d));
     g_nwx_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  // ---- heads (fp32 CUDA-core passes over d_raw / hv / h8): small, latency-bound kernels that write their own,
+  // disjoint part of the gradient buffer.  On their own stream, forked BEHIND the dX kernel (whose CTAs fill the
+  // shared memory of every SM), they run underneath the dW kernel -- its CTAs leave 30 KB of shared memory and 1 500
+  // threads per SM free -- instead of after it.
+  {
+    const cudaStream_t hs = heads_st ? heads_st : st;
+    if (heads_st) {
+      NWX_CUDA_TRY(cudaEventRecord(fork, st));                 // behind dX: inputs ready, gradients zeroed, SMs about to run dW
+      NWX_CUDA_TRY(cudaStreamWaitEvent(heads_st, fork, 0));
+    }
+    HeadArgs h{};
+    const int64_t n_rays = a.P / a.S;
+    const int segs = (a.S + kSegPoints - 1) / kSegPoints;
+    const int64_t n_units = n_rays * segs;
+    h.d_raw = a.d_raw; h.hv = a.hv; h.acts = a.acts; h.pe_dir = a.pe_dir; h.gconsts = net.gconsts;
+    h.head_partial = a.head_partial; h.gsum = a.head_partial + head_rows(tiles, n_units) * kHeadOut;
+    h.P = a.P; h.n_tiles = tiles; h.n_rays = n_rays; h.S = a.S; h.segs = segs;
+    const int n_rgb = head_rgb_blocks(n_units);
+    const int n_dir = (int)((n_units + kDirUnitsPerBlock - 1) / kDirUnitsPerBlock);
+    const int n_sigma = (int)((tiles + kSigmaTilesPerBlock - 1) / kSigmaTilesPerBlock);
+    head_rgb_kernel<<<n_rgb, 256, 0, hs>>>(h);
+    NWX_LAUNCHED();
+    head_dir_kernel<<<n_dir, kViewHidden, 0, hs>>>(h);
+    NWX_LAUNCHED();
+    head_sigma_kernel<<<n_sigma, 256, 0, hs>>>(h);
+    NWX_LAUNCHED();
+    reduce_heads_kernel<<<(kHeadValid + 31) / 32, 256, 0, hs>>>(a.head_partial, n_rgb, n_dir, n_sigma, a.grad, g_flat.off[16],
+                                                               g_flat.off[20], g_flat.off[21], g_flat.off[22], g_flat.off[23]);
+    NWX_LAUNCHED();
+    if (heads_st) NWX_CUDA_TRY(cudaEventRecord(join, heads_st));
   }
   // ---- dW ----
   int grid = 0;
@@ -1155,25 +1187,7 @@ int launch_mlp_backward(const PackedNet& net, const TrainBwdArgs& a, cudaStream_
                                                                                    a.grad + off[16]);
     NWX_LAUNCHED();
   }
-  HeadArgs h{};
-  const int64_t n_rays = a.P / a.S;
-  const int segs = (a.S + kSegPoints - 1) / kSegPoints;
-  const int64_t n_units = n_rays * segs;
-  h.d_raw = a.d_raw; h.hv = a.hv; h.acts = a.acts; h.pe_dir = a.pe_dir; h.gconsts = net.gconsts;
-  h.head_partial = a.head_partial; h.gsum = a.head_partial + head_rows(tiles, n_units) * kHeadOut;
-  h.P = a.P; h.n_tiles = tiles; h.n_rays = n_rays; h.S = a.S; h.segs = segs;
-  const int n_rgb = head_rgb_blocks(n_units);
-  const int n_dir = (int)((n_units + kDirUnitsPerBlock - 1) / kDirUnitsPerBlock);
-  const int n_sigma = (int)((tiles + kSigmaTilesPerBlock - 1) / kSigmaTilesPerBlock);
-  head_rgb_kernel<<<n_rgb, 256, 0, st>>>(h);
-  NWX_LAUNCHED();
-  head_dir_kernel<<<n_dir, kViewHidden, 0, st>>>(h);
-  NWX_LAUNCHED();
-  head_sigma_kernel<<<n_sigma, 256, 0, st>>>(h);
-  NWX_LAUNCHED();
-  reduce_heads_kernel<<<(kHeadValid + 31) / 32, 256, 0, st>>>(a.head_partial, n_rgb, n_dir, n_sigma, a.grad, g_flat.off[16],
-                                                             g_flat.off[20], g_flat.off[21], g_flat.off[22], g_flat.off[23]);
-  NWX_LAUNCHED();
+  if (heads_st) NWX_CUDA_TRY(cudaStreamWaitEvent(st, join, 0));      // the network's gradient is final on `st` from here on
   return NWX_OK;
 }
 
