@@ -46,13 +46,20 @@ def main():
         parts = [eng.render_rays(rays[a:b], want=("rgb_fine",))["rgb_fine"] for a, b in zip(cuts[:-1], cuts[1:])]
         return torch.cat(parts, 0).reshape(-1)
     cases["sharded_render_vs_full_frame"] = shards
+    # the full set of outputs the render test asks for (weights, merged depths, maps, uint8 pixels), all compared
+    want = ("rgb_fine", "acc_fine", "depth_fine", "z_vals_fine", "weights_fine", "rgb8_fine")
+
+    def full_outputs():
+        o = eng.render_rays(rays, want=want)
+        return torch.cat([o[k].reshape(-1).view(torch.uint8) for k in want])
+    cases["render_rays_all_outputs"] = full_outputs
     res = {}
     for name, fn in cases.items():
         ref = full.reshape(-1) if name.startswith("sharded") else fn().clone()
         bad, worst = 0, 0
         for _ in range(args.iters):
             cur = fn()
-            diff = int((cur.view(torch.int32) != ref.view(torch.int32)).sum())
+            diff = int((cur != ref).sum()) if cur.dtype == torch.uint8 else int((cur.view(torch.int32) != ref.view(torch.int32)).sum())
             if diff:
                 bad += 1
                 worst = max(worst, diff)
