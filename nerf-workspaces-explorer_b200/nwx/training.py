@@ -6,6 +6,7 @@ data-parallel gradient all-reduce on torch.distributed (NCCL).  Dataset loading,
 renders and checkpoint writing stay with the caller (out of scope)."""
 from __future__ import annotations
 
+import os
 import ctypes as C
 from typing import Dict, Mapping, Optional, Tuple
 
@@ -92,7 +93,8 @@ class Trainer:
             dist.broadcast(self.params, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         # data-parallel overlap: the coarse network's gradients are complete before the fine network's
         # backward starts, so their all-reduce runs on a side stream underneath it
-        self._overlap = bool(overlap_allreduce) and self.world > 1 and self.device.type == "cuda"
+        self._overlap = (bool(overlap_allreduce) and self.world > 1 and self.device.type == "cuda"
+                         and os.environ.get("NWX_TRAIN_OVERLAP", "1") != "0")      # env: A/B switch for measurements
         self._comm_stream = torch.cuda.Stream(self.device) if self._overlap else None
         self._ev_coarse = torch.cuda.Event() if self._overlap else None
         self._coarse_reduced = False
