@@ -78,6 +78,22 @@ coarse_z_kernel(const float* __restrict__ rays, int ray_dim, int64_t total, int 
   }
 }
 
+// The render path's case (no jitter, S % 4 == 0, 16-byte aligned output): thread = four consecutive samples of a
+// ray, one 128-bit store; the same correctly rounded expression per element as coarse_z_kernel.
+__global__ void __launch_bounds__(256)
+coarse_z_det4_kernel(const float* __restrict__ rays, int ray_dim, int64_t total4, int S4,
+                     const float* __restrict__ t_vals, float4* __restrict__ z_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const int64_t n = i / S4;
+    const int s4 = (int)(i - n * S4);
+    const float near = __ldg(rays + n * ray_dim + 6), far = __ldg(rays + n * ray_dim + 7);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(t_vals) + s4);
+    auto zlin = [&](float tk) { return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, tk)), __fmul_rn(far, tk)); };
+    z_out[i] = make_float4(zlin(t.x), zlin(t.y), zlin(t.z), zlin(t.w));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 to8b_kernel(const float* __restrict__ x, int64_t n, uint8_t* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -154,8 +170,16 @@ int nwx::launch_coarse_z(const float* rays, int ray_dim, int64_t N, int S, const
   if (N == 0) return NWX_OK;                     // empty shard: pointers may be null
   NWX_REQUIRE(rays && t_vals && z_out);
   const int64_t total = N * S;
-  int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)nwx::num_sms() * 16;
+  if (t_rand == nullptr && !rng.on && S % 4 == 0 && ((uintptr_t)z_out & 15) == 0 && ((uintptr_t)t_vals & 15) == 0) {
+    int64_t blocks = (total / 4 + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    nwx::coarse_z_det4_kernel<<<(unsigned)blocks, 256, 0, st>>>(rays, ray_dim, total / 4, S / 4, t_vals,
+                                                               reinterpret_cast<float4*>(z_out));
+    NWX_LAUNCHED();
+    return NWX_OK;
+  }
+  int64_t blocks = (total + 255) / 256;
   if (blocks > cap) blocks = cap;
   nwx::coarse_z_kernel<<<(unsigned)blocks, 256, 0, st>>>(rays, ray_dim, total, S, t_vals, t_rand, rng, z_out);
   NWX_LAUNCHED();

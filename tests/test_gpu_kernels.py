@@ -55,6 +55,9 @@ def test_coarse_z_bit_exact(eng):
         ref = orc.coarse_z(rays, 64, tr)
         got = eng.coarse_z(rays.to(DEV), 64, None if tr is None else tr.to(DEV))
         assert bits_equal(got.cpu(), ref.contiguous())
+    for S in (2, 6, 8, 33, 100):               # S % 4 == 0 takes the 128-bit-store kernel, the others the scalar one
+        assert bits_equal(eng.coarse_z(rays.to(DEV), S, None).cpu(), orc.coarse_z(rays, S, None).contiguous()), S
+        assert bits_equal(eng.coarse_z(rays[:1].to(DEV), S, None).cpu(), orc.coarse_z(rays[:1], S, None).contiguous()), S
 
 
 def test_embed_and_to8b():
