@@ -667,54 +667,79 @@ int pack_network(PackedNet& net, const float* const* t, cudaStream_t st) {
 
 // dirbias[n][j] = b_view[j] + sum_i W_view[j][256+i] * pe_dir(dir_n)[i]   (fp32)
 // pe_dir = Embedding(num_freqs=4, scalar_factor=1).embed  (embedding.py:44-48)
-__global__ void __launch_bounds__(kViewHidden)
+// Register-tiled: a warp owns 32 rays and all 128 columns; lane = four adjacent columns with their 4 x 27 weights in
+// registers.  The warp's embeddings sit feature-major in its own shared-memory slice ([feature][ray]); per feature ONE
+// broadcast LDS.128 brings four rays and feeds 16 FMAs (8 packed fp32x2, the weight as the broadcast scalar), so the
+// shared-memory return path (the limit of a thread-per-column layout: one LDS.128 per 4 FMAs) is no longer the bound.
+// Per (ray, column) the sum runs i = 0 .. 26 from the bias, each term one IEEE fma; one STG.128 per ray and lane.
+constexpr int kDirbiasWarps = 4, kDirbiasRays = 32 * kDirbiasWarps;
+__global__ void __launch_bounds__(32 * kDirbiasWarps)
 dirbias_kernel(const float* __restrict__ dirs, int stride, int64_t n, int pre_embedded,
                const float* __restrict__ wdir_t, const float* __restrict__ bview, float* __restrict__ out) {
-  // thread = output column j with its 27 weights in registers; 32 rays per block, their embeddings in shared
-  // memory as 7 float4 each (27 + one zero), read as broadcast LDS.128: 7 loads + 27 FMAs per output.
-  constexpr int kRays = 32, kQ = (kPeDir + 3) / 4;
-  __shared__ float4 pe4[kRays][kQ];
-  float* pe = reinterpret_cast<float*>(&pe4[0][0]);
-  const int64_t base = (int64_t)blockIdx.x * kRays;
-  for (int e = threadIdx.x; e < kRays * 4 * kQ; e += blockDim.x) {
-    const int r = e / (4 * kQ), i = e - r * (4 * kQ);
-    const int64_t ray = base + r < n ? base + r : n - 1;
-    float v = 0.0f;
-    if (i < kPeDir) {
-      if (pre_embedded || i < 3) v = __ldg(dirs + ray * stride + i);
-      else {
-        const int k = (i - 3) / 6, w = (i - 3) % 6, a = w % 3;
-        const float x = __ldg(dirs + ray * stride + a) * (float)(1 << k);
-        v = (w < 3) ? sinf(x) : cosf(x);
+  constexpr int kF = 27;
+  __shared__ float4 pe4[kDirbiasWarps][kF][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)blockIdx.x * kDirbiasRays + warp * 32;
+  if (base >= n) return;                                         // no block-wide barrier below
+  float* pe = reinterpret_cast<float*>(&pe4[warp][0][0]);       // [feature][ray of the warp]
+  {
+    const int64_t ray = base + lane < n ? base + lane : n - 1;
+    const float* d = dirs + ray * stride;
+    if (pre_embedded) {
+#pragma unroll
+      for (int i = 0; i < kF; ++i) pe[i * 32 + lane] = __ldg(d + i);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float x = __ldg(d + a);
+        pe[a * 32 + lane] = x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                            // sin and cos of 2^k x from one range reduction
+          float sn, cs;
+          sincosf(x * (float)(1 << k), &sn, &cs);
+          pe[(3 + 6 * k + a) * 32 + lane] = sn;
+          pe[(6 + 6 * k + a) * 32 + lane] = cs;
+        }
       }
     }
-    pe[e] = v;
   }
-  const int j = threadIdx.x;
-  float w[4 * kQ];
+  float4 w[kF];
 #pragma unroll
-  for (int i = 0; i < 4 * kQ; ++i) w[i] = i < kPeDir ? __ldg(wdir_t + i * kViewHidden + j) : 0.0f;
-  const float b = __ldg(bview + j);
-  __syncthreads();
-#pragma unroll 4
-  for (int r = 0; r < kRays; ++r) {
-    float acc = b;                                  // same summation order as before: i = 0 .. 26
+  for (int i = 0; i < kF; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(wdir_t + i * kViewHidden) + lane);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bview) + lane);
+  const uint32_t pe_addr = smem_u32(pe);
+  __syncwarp();
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {                                  // four rays at a time
+    uint64_t acc[4][2];                                          // [column][ray pair]
+    acc[0][0] = acc[0][1] = f32x2(b.x, b.x);
+    acc[1][0] = acc[1][1] = f32x2(b.y, b.y);
+    acc[2][0] = acc[2][1] = f32x2(b.z, b.z);
+    acc[3][0] = acc[3][1] = f32x2(b.w, b.w);
 #pragma unroll
-    for (int q = 0; q < kQ; ++q) {
-      const float4 p = pe4[r][q];
-      acc = fmaf(w[4 * q + 0], p.x, acc);
-      acc = fmaf(w[4 * q + 1], p.y, acc);
-      acc = fmaf(w[4 * q + 2], p.z, acc);
-      if (4 * q + 3 < kPeDir) acc = fmaf(w[4 * q + 3], p.w, acc);
+    for (int i = 0; i < kF; ++i) {
+      uint64_t v0, v1;                                           // feature i of rays (4g, 4g + 1), (4g + 2, 4g + 3)
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(pe_addr + (uint32_t)((i * 8 + g) * 16)) : "memory");
+      const float wc[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[c][0] = ffma2(f32x2(wc[c], wc[c]), v0, acc[c][0]);
+        acc[c][1] = ffma2(f32x2(wc[c], wc[c]), v1, acc[c][1]);
+      }
     }
-    if (base + r < n) out[(base + r) * kViewHidden + j] = acc;
+    float4* o = reinterpret_cast<float4*>(out + (base + 4 * g) * kViewHidden) + lane;
+    const int64_t left = n - (base + 4 * g);
+    if (left > 0) o[0] = make_float4(f32x2_lo(acc[0][0]), f32x2_lo(acc[1][0]), f32x2_lo(acc[2][0]), f32x2_lo(acc[3][0]));
+    if (left > 1) o[32] = make_float4(f32x2_hi(acc[0][0]), f32x2_hi(acc[1][0]), f32x2_hi(acc[2][0]), f32x2_hi(acc[3][0]));
+    if (left > 2) o[64] = make_float4(f32x2_lo(acc[0][1]), f32x2_lo(acc[1][1]), f32x2_lo(acc[2][1]), f32x2_lo(acc[3][1]));
+    if (left > 3) o[96] = make_float4(f32x2_hi(acc[0][1]), f32x2_hi(acc[1][1]), f32x2_hi(acc[2][1]), f32x2_hi(acc[3][1]));
   }
 }
 
 int launch_dirbias(const PackedNet& net, const float* dirs, int stride, int64_t n, bool pre_embedded, bool fold,
                    float* out, cudaStream_t st) {
   if (n == 0) return NWX_OK;
-  dirbias_kernel<<<(unsigned)((n + 31) / 32), kViewHidden, 0, st>>>(dirs, stride, n, pre_embedded ? 1 : 0, net.wdir_t,
+  dirbias_kernel<<<(unsigned)((n + kDirbiasRays - 1) / kDirbiasRays), kViewHidden, 0, st>>>(dirs, stride, n, pre_embedded ? 1 : 0, net.wdir_t,
                                                                  fold ? net.bview_fold : net.bview, out);
   NWX_LAUNCHED();
   return NWX_OK;
