@@ -22,7 +22,7 @@ timeout 1200 ncu --set full --clock-control none --import-source on \
     -s 70 -c 16 -o $OUT/prof_train -f python tools/train_bench.py --steps 4 > $OUT/ncu_train_full.log 2>&1
 echo "ncu train full rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k "regex:composite_fwd|sample_pdf|dirbias_kernel|coarse_z_kernel|raygen_kernel" -s 12 -c 7 \
+    -k "regex:composite_fwd|sample_pdf|dirbias_kernel|coarse_z|raygen_kernel" -s 12 -c 7 \
     -o $OUT/prof_small -f python bench.py --steps 2 --warmup 3 > $OUT/ncu_small.log 2>&1
 echo "ncu small rc=$?"
 if [ "${FULL_MLP:-0}" = "1" ]; then
