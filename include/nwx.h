@@ -266,7 +266,9 @@ int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped);
  * image, 1 transposed image (dX), 2 device-side constants, 3 view-direction table, 4 views bias, 5 folded views bias. */
 int nwx_debug_copy_packed(nwx_ctx* ctx, int which, int what, void* dst, int64_t bytes, void* stream);
 /* Timing experiments in the training kernels (results wrong on purpose; tools/train_experiments.py): 0 = none,
- * 11 = epilogues do not wait for their tile's previous TMA store, 12 = no TMA stores of the tile images. */
+ * 11 = epilogues do not wait for their tile's previous TMA store, 12 = no TMA stores of the tile images, 13-15 see
+ * csrc/context.cu.  Compiled in only by `make EXPERIMENTS=1`; the product library returns NWX_E_INVALID for any
+ * code but 0. */
 int nwx_debug_experiment(nwx_ctx* ctx, int code);
 /* The 4 diagnostic words (0xDEADxxxx | waiter code, block, barrier, parity) of the last aborted wait; zeros
  * if none.  Every context owns such a host-mapped word from creation (nwx_debug_diag(ctx, NULL) restores

@@ -428,8 +428,8 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (kTrain) {
             // the TMA store that saved this buffer's previous contents must have finished reading it
             // (groups complete in order: all but the newest one, which belongs to the other tile)
-            if (warp == 8 && lane == 0 && args.experiment == 0) bulk_wait_read<1>();
-            if (args.experiment != 14) named_bar_sync(3, 256);
+            if (warp == 8 && lane == 0 && NWX_EXP(args) == 0) bulk_wait_read<1>();
+            if (NWX_EXP(args) != 14) named_bar_sync(3, 256);
           }
           float* tap_row = nullptr;
           if (kTap && args.dbg_out != nullptr && args.dbg_layer == l && p < P) tap_row = args.dbg_out + p * kHidden;
@@ -439,7 +439,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
             const uint32_t hrow = (kTap && args.dbg_layer == -3 && args.dbg_out != nullptr)
                                       ? 0u : sbase + L::h0 + t * kHBytes + row * 128;
             uint8_t* mask_row = nullptr;         // training: ReLU' bit words of (tile, layer l), see mask_img_offset
-            if (kTrain && args.masks != nullptr && l < 8 && args.experiment != 13)
+            if (kTrain && args.masks != nullptr && l < 8 && NWX_EXP(args) != 13)
               mask_row = reinterpret_cast<uint8_t*>(args.masks) +
                          mask_img_offset(tile_of(it, t) < args.n_tiles ? tile_of(it, t) : args.n_tiles, l);
             const bool dbg_half = kTap && args.dbg_layer == -7 && args.dbg_out != nullptr;
@@ -485,7 +485,7 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
                   g2 = ffma2(hv2, q ? pair(wgq.z, wgq.w) : pair(wgq.x, wgq.y), g2);
                   b2 = ffma2(hv2, q ? pair(wb.z, wb.w) : pair(wb.x, wb.y), b2);
                 }
-                if (kTrain && args.hv_out != nullptr && p < P && args.experiment != 15)      // post-ReLU views hidden, for the backward
+                if (kTrain && args.hv_out != nullptr && p < P && NWX_EXP(args) != 15)      // post-ReLU views hidden, for the backward
                   *reinterpret_cast<float4*>(args.hv_out + p * kViewHidden + col + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
               }
             }
@@ -520,8 +520,8 @@ mlp_fused_kernel(const __grid_constant__ MlpArgs args, const __grid_constant__ M
           if (kTrain && l < 9) {
             // training: the activation tile just written IS the image the backward wants -- one TMA
             // store of the whole 64 KB tile instead of 16 global stores per thread
-            if (args.experiment != 14) named_bar_sync(3, 256);              // every warp's tile writes are fenced
-            if (warp == 8 && lane == 0 && args.acts != nullptr && tile_of(it, t) < args.n_tiles && args.experiment != 12)
+            if (NWX_EXP(args) != 14) named_bar_sync(3, 256);              // every warp's tile writes are fenced
+            if (warp == 8 && lane == 0 && args.acts != nullptr && tile_of(it, t) < args.n_tiles && NWX_EXP(args) != 12)
               bulk_s2g(args.acts + tile_img_offset(act_slot_kb0(l + 1), 4, args.n_tiles, tile_of(it, t), 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
           }

@@ -74,6 +74,14 @@ struct PackedNet {
   bool consts_stale = false;         // host consts older than the device master weights (training)
 };
 
+// Timing experiments (tools/train_experiments.py; results wrong on purpose) exist only in builds made with
+// `make EXPERIMENTS=1`; in the product build the switch is the constant 0 and the branches disappear.
+#ifdef NWX_EXPERIMENTS
+#define NWX_EXP(args) ((args).experiment)
+#else
+#define NWX_EXP(args) 0
+#endif
+
 struct MlpArgs {
   const float* rays;                 // [N, ray_dim] or nullptr (points mode)
   const float* z;                    // [N, S]

@@ -376,8 +376,8 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           // TMA store; the last two store per thread: after the last MMA the G_views producers reuse the
           // buffer, and they cannot wait on another thread's bulk group.
           const bool via_tma = s < kDxSteps - 2;
-          if (warp == 8 && lane == 0 && args.experiment == 0) bulk_wait_read<1>();   // earlier store of this buffer has finished reading it
-          if (args.experiment != 14) named_bar_sync(3, 256);
+          if (warp == 8 && lane == 0 && NWX_EXP(args) == 0) bulk_wait_read<1>();   // earlier store of this buffer has finished reading it
+          if (NWX_EXP(args) != 14) named_bar_sync(3, 256);
           if (s == 0) bwd_epilogue<kBwdSigmaMask>(cst, d_tmem, hrow, true, false, row, wg, mreg[t], grow, dsig[t]);
           else bwd_epilogue<kBwdMask>(cst, d_tmem, hrow, s != kDxSteps - 1, !via_tma, row, wg, mreg[t], grow, 0.f);
           // next use of this tile slot: step s + 1 of the same tile, or step 0 of the next iteration's tile
@@ -388,8 +388,8 @@ mlp_bwd_dx_kernel(const __grid_constant__ DxArgs args) {
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(leader(sbase + L::a_ready + 8 * t));
           if (via_tma) {
-            if (args.experiment != 14) named_bar_sync(3, 256);                             // every warp's tile writes are fenced
-            if (warp == 8 && lane == 0 && args.experiment != 12)
+            if (NWX_EXP(args) != 14) named_bar_sync(3, 256);                             // every warp's tile writes are fenced
+            if (warp == 8 && lane == 0 && NWX_EXP(args) != 12)
               bulk_s2g(args.grads + tile_img_offset(grad_slot_kb0(s + 2), 4, args.n_tiles + 1, wt, 0),
                        sbase + L::h0 + t * kHBytes, kHBytes);
           }

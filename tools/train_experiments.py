@@ -7,7 +7,9 @@ kernels' timing experiments switched on (nwx_debug_experiment; gradients are WRO
   13  the forward neither builds nor stores the ReLU' bit masks
   14  no named barriers around the tile writes (the store's wait is skipped too)
   15  the forward does not store the views hidden
-Prints one JSON line with ms per step and the per-kernel CUDA-event times of forward, dX and the rest."""
+Prints one JSON line with ms per step and the per-kernel CUDA-event times of forward, dX and the rest.
+Needs a library built with the experiments compiled in:  make -C nerf-workspaces-explorer_b200 clean && make -C
+nerf-workspaces-explorer_b200 EXPERIMENTS=1  (the product build has no such branches and rejects the codes)."""
 import json
 import os
 import sys
