@@ -267,3 +267,31 @@ def test_other_sampling_config_32_plus_64():
     assert torch.equal(out["z_vals_coarse"].cpu(), ref["z_vals_coarse"].contiguous())
     for k in ("rgb_fine", "rgb_coarse", "acc_fine"):
         assert float((out[k].cpu() - ref[k]).abs().max()) <= 1e-3, k
+
+
+def test_white_background_and_odd_sample_counts():
+    """`white_bkgd=True` (raw2outputs, model_utils.py:97-98) through the whole render, at the shipped 64+128 and at
+    sample counts that are no multiple of anything (50 + 77: the generic resampling / compositing kernels, a ragged
+    last MLP tile): rgb / acc within 1e-3 of the oracle, coarse depths exact, uint8 pixels = to8b(rgb_fine)."""
+    import nwx
+    from nwx import engine as E
+    sd_c, sd_f = _nets()
+    eng = nwx.Engine(torch.device(DEV))
+    eng.load_weights(E.COARSE, sd_c); eng.load_weights(E.FINE, sd_f)
+    rays = load_golden("render_infer")["rays"]
+    for sc, ni in ((64, 128), (50, 77)):
+        cfg = orc.RenderConfig(n_samples=sc, n_importance=ni, white_bkgd=True)
+        with torch.no_grad():
+            ref = orc.volumetric_rendering(rays, sd_c, sd_f, cfg, train_mode=False)
+        out = eng.render_rays(rays.to(DEV), sc, ni, True,
+                              want=("rgb_fine", "rgb_coarse", "acc_fine", "acc_coarse", "z_vals_coarse", "z_vals_fine", "rgb8_fine"))
+        assert out["z_vals_fine"].shape == (rays.shape[0], sc + ni)
+        assert torch.equal(out["z_vals_coarse"].cpu(), ref["z_vals_coarse"].contiguous())
+        for k in ("rgb_fine", "rgb_coarse", "acc_fine", "acc_coarse"):
+            err = float((out[k].cpu() - ref[k]).abs().max())
+            assert err <= 1e-3, (sc, ni, k, err)
+        # the background term is really there: rays that are not opaque come out brighter than without it
+        plain = eng.render_rays(rays.to(DEV), sc, ni, False, want=("rgb_fine", "acc_fine"))
+        gain = (out["rgb_fine"] - plain["rgb_fine"]).mean(-1) - (1.0 - plain["acc_fine"])
+        assert float(gain.abs().max()) <= 1e-5
+        assert torch.equal(out["rgb8_fine"].cpu(), torch.from_numpy(orc.to8b(out["rgb_fine"].cpu().numpy())))
