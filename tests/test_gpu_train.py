@@ -308,14 +308,21 @@ def test_gradients_white_background_and_other_sample_counts():
     rays, gt = g["rays"], g["gt"].float()
     n = rays.shape[0]
     gen = torch.Generator().manual_seed(17)
-    for sc, ni, wb in ((64, 128, True), (48, 80, False)):
+    for sc, ni, wb, perturb in ((64, 128, True, 1.0), (48, 80, False, 1.0), (64, 128, False, 0.0)):
         t_rand, u = torch.rand(n, sc, generator=gen), torch.rand(n, ni, generator=gen)
         nc, nf = torch.randn(n, sc, generator=gen), torch.randn(n, sc + ni, generator=gen)
         sd_c, sd_f = _nets()
-        cfg = orc.RenderConfig(n_samples=sc, n_importance=ni, white_bkgd=wb)
-        lc, lf, gc, gf, _ = orc.training_loss_and_grads(rays, gt, sd_c, sd_f, cfg, t_rand, u, nc, nf)
-        tr = nwx.Trainer(nwx.Engine(torch.device(DEV)), sd_c, sd_f, n_samples=sc, n_importance=ni, white_bkgd=wb)
-        loss = tr.forward_backward(rays.to(DEV), gt.to(DEV), t_rand.to(DEV), u.to(DEV), nc.to(DEV), nf.to(DEV))
+        if perturb == 0.0:            # perturb = 0, raw_noise_std = 0 (training handler:547-578): no draws at all
+            cfg = orc.RenderConfig(n_samples=sc, n_importance=ni, white_bkgd=wb, perturb=0.0, raw_noise_std=0.0)
+            lc, lf, gc, gf, _ = orc.training_loss_and_grads(rays, gt, sd_c, sd_f, cfg, None, None, None, None)
+            tr = nwx.Trainer(nwx.Engine(torch.device(DEV)), sd_c, sd_f, n_samples=sc, n_importance=ni, white_bkgd=wb,
+                             perturb=0.0, raw_noise_std=0.0)
+            loss = tr.forward_backward(rays.to(DEV), gt.to(DEV))
+        else:
+            cfg = orc.RenderConfig(n_samples=sc, n_importance=ni, white_bkgd=wb)
+            lc, lf, gc, gf, _ = orc.training_loss_and_grads(rays, gt, sd_c, sd_f, cfg, t_rand, u, nc, nf)
+            tr = nwx.Trainer(nwx.Engine(torch.device(DEV)), sd_c, sd_f, n_samples=sc, n_importance=ni, white_bkgd=wb)
+            loss = tr.forward_backward(rays.to(DEV), gt.to(DEV), t_rand.to(DEV), u.to(DEV), nc.to(DEV), nf.to(DEV))
         assert abs(float(loss[0]) - float(lc)) <= 1e-5 * float(lc) and abs(float(loss[1]) - float(lf)) <= 1e-5 * float(lf)
         worst_ratio, worst_cos = 0.0, 1.0
         for which, ref in ((0, gc), (1, gf)):
@@ -323,5 +330,5 @@ def test_gradients_white_background_and_other_sample_counts():
                 a, b = grad.cpu().double().reshape(-1), ref[k].double().reshape(-1)
                 ratio, cos = float(a.norm() / b.norm()), float((a @ b) / (a.norm() * b.norm()))
                 worst_ratio, worst_cos = max(worst_ratio, abs(ratio - 1.0)), min(worst_cos, cos)
-                assert abs(ratio - 1.0) <= 0.03 and cos >= 0.993, (sc, ni, wb, which, k, ratio, cos)   # measured 1.3 %, 0.9949
-        print(f"{sc}+{ni} white_bkgd={wb}: worst |norm ratio - 1| {worst_ratio:.4f}, worst cosine {worst_cos:.5f}")
+                assert abs(ratio - 1.0) <= 0.03 and cos >= 0.993, (sc, ni, wb, perturb, which, k, ratio, cos)   # measured 1.3 %, 0.9949
+        print(f"{sc}+{ni} white_bkgd={wb} perturb={perturb}: worst |norm ratio - 1| {worst_ratio:.4f}, worst cosine {worst_cos:.5f}")
