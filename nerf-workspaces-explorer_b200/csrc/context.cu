@@ -193,11 +193,12 @@ extern "C" int nwx_debug_diag(nwx_ctx* ctx, uint32_t* host_mapped) {
 // Timing experiments in the training forward / dX kernels (tools/train_experiments.py); results are WRONG on purpose:
 // 11 = the epilogues do not wait for the previous TMA store of their tile, 12 = no TMA stores of the tile images at all,
 // 13 = the forward neither builds nor stores the ReLU' bit masks, 14 = no named barriers around the tile writes (and 11),
-// 15 = the forward does not store the views hidden.
+// 15 = the forward does not store the views hidden, 18 = the training forward saves nothing at all (the kTrain
+// instantiation with null save pointers: what the operands' way to HBM costs in total).
 // Only a library built with `make EXPERIMENTS=1` contains them; the product build accepts code 0 alone.
 extern "C" int nwx_debug_experiment(nwx_ctx* ctx, int code) {
 #ifdef NWX_EXPERIMENTS
-  NWX_REQUIRE(ctx && (code == 0 || (code >= 11 && code <= 15)));
+  NWX_REQUIRE(ctx && (code == 0 || (code >= 11 && code <= 15) || code == 18));
 #else
   NWX_REQUIRE(ctx && code == 0);
 #endif
@@ -514,6 +515,9 @@ extern "C" int nwx_train_fwd_bwd(nwx_ctx* ctx, const nwx_train_io* io, int64_t N
     a.rays = io->rays; a.z = z; a.wimg = net.wimg; a.dirbias = dirb; a.raw_out = raw; a.diag = ctx->diag;
     a.acts = acts[which]; a.masks = masks[which]; a.hv_out = hv[which]; a.P = N * S; a.ray_dim = rd; a.S = S;
     a.experiment = ctx->experiment;
+#ifdef NWX_EXPERIMENTS
+    if (ctx->experiment == 18) { a.acts = nullptr; a.masks = nullptr; a.hv_out = nullptr; }
+#endif
     return nwx::launch_mlp_train_forward(net, a, st);
   };
   const nwx::RngSpec rj = rng_for(o, 0, o->t_rand, o->rng_jitter != 0), ru = rng_for(o, 1, o->u, o->rng_u != 0);

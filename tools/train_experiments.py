@@ -7,6 +7,7 @@ kernels' timing experiments switched on (nwx_debug_experiment; gradients are WRO
   13  the forward neither builds nor stores the ReLU' bit masks
   14  no named barriers around the tile writes (the store's wait is skipped too)
   15  the forward does not store the views hidden
+  18  the training forward saves nothing at all (null save pointers)
 Prints one JSON line with ms per step and the per-kernel CUDA-event times of forward, dX and the rest.
 Needs a library built with the experiments compiled in:  make -C nerf-workspaces-explorer_b200 clean && make -C
 nerf-workspaces-explorer_b200 EXPERIMENTS=1  (the product build has no such branches and rejects the codes)."""
@@ -35,7 +36,8 @@ def main():
     rays = bank[torch.randint(0, bank.shape[0], (4096,), device=dev, generator=gen)]
     gt = torch.rand((4096, 3), device=dev, generator=gen)
     out = {}
-    for code in (0, 11, 12, 13, 14, 15, 0):
+    codes = [int(c) for c in sys.argv[1:]] or [0, 11, 12, 13, 14, 15, 18, 0]
+    for code in codes:
         check(nwx.lib().nwx_debug_experiment(eng._ctx, code))
         for i in range(3):
             tr.forward_backward(rays, gt)
